@@ -1,0 +1,103 @@
+"""ctypes binding of libb200det.so (the C ABI declared in include/b200det.h).
+
+There is no CPU implementation and no fallback: if the shared library is
+missing or a tensor is not on a CUDA device, the call raises.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200det.so")
+
+B200_LAYOUT_NCHW = 0
+B200_LAYOUT_NHWC = 1
+B200_MAX_LEVELS = 8
+B200_NMS_MAX_SEG = 16384
+B200_MATCH_SOFTMAX = 0
+B200_MATCH_COLMAX = 1
+
+
+class b200_level(ctypes.Structure):
+    _fields_ = [("data", ctypes.c_void_p), ("height", ctypes.c_int32),
+                ("width", ctypes.c_int32), ("spatial_scale", ctypes.c_float)]
+
+
+_lib = None
+
+_vp, _i, _i64, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t
+
+# name -> (restype, argtypes); must list every symbol include/b200det.h declares
+SIGNATURES = {
+    "b200_version": (_i, []),
+    "b200_last_error_string": (ctypes.c_char_p, []),
+    "b200_roi_align_forward": (_i, [ctypes.POINTER(b200_level), _i, _i, _i, _i, _vp, _i64, _i, _i, _i, _vp, _vp, _vp]),
+    "b200_roi_align_backward": (_i, [ctypes.POINTER(b200_level), _i, _i, _i, _i, _vp, _i64, _i, _i, _i, _vp, _vp]),
+    "b200_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "b200_nhwc_to_nchw": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "b200_nms_workspace_bytes": (_sz, [_i64, _i64, _i64]),
+    "b200_nms_batched": (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _f, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "b200_embed_match": (_i, [_vp, _vp, _i64, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200_colmax_decode": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
+    "b200_roi_pool_forward": (_i, [_vp, _i, _i, _i, _i, _vp, _i64, _f, _i, _i, _vp, _vp, _vp]),
+    "b200_roi_pool_backward": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+}
+
+
+def lib():
+    """Load (once) and return the shared library; raise if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "%s is missing: build it with `python -m cvpr22_cross_modal_pseudo_labeling_b200.build` "
+                "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        if hasattr(l, "b200_debug_set"):
+            l.b200_debug_set.restype = None
+            l.b200_debug_set.argtypes = [_i, _i, _i]
+        if hasattr(l, "b200_debug_nms"):
+            l.b200_debug_nms.restype = None
+            l.b200_debug_nms.argtypes = [_i]
+        _lib = l
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().b200_last_error_string().decode(errors="replace")
+        if rc == -1:
+            raise ValueError("%s: %s" % (what, msg))
+        raise RuntimeError("%s failed (status %d): %s" % (what, rc, msg))
+
+
+def require_cuda(t, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor (the B200 path has no CPU implementation)" % name)
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def stream_ptr(device=None):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def debug_set(force_generic=False, exact=True, variant=0):
+    """Tuning / test hook: select the generic RoIAlign kernel, the FMA variant,
+    or the staged kernel's patch budget."""
+    lib().b200_debug_set(int(force_generic), int(exact), int(variant))
+
+
+def debug_nms(force_bitmask=False):
+    """Test hook: force the three-kernel bitmask NMS path (default: fused kernel when the
+    longest segment fits in shared memory)."""
+    lib().b200_debug_nms(int(force_bitmask))

@@ -1,0 +1,549 @@
+// nms.cu -- batched (segmented) greedy NMS for sm_100a.
+//
+// Replaces _C.nms (reference csrc/nms.h:10-28; CPU kernel csrc/cpu/nms_cpu.cpp:6-65,
+// CUDA kernel csrc/cuda/nms.cu:23-130) and the per-(image,level) / per-(image,class)
+// Python loops around it.  Semantics follow the CPU file: legacy "+1" extents,
+// suppress when IoU >= thresh, every fp32 operation rounded on its own
+// (the _rn intrinsics below are never contracted into FMAs).
+//
+// Three kernels, all segments of a batch per launch, nothing returns to the host:
+//   1. nms_sort_kernel   one CTA per segment: (score desc, index asc) order by an
+//                        in-shared-memory bitonic sort of 64-bit keys; skipped when the
+//                        segment is already ordered (RPN top-k output is).
+//   2. nms_mask_kernel   64x64 IoU tiles of the upper triangle -> one 64-bit suppression
+//                        word per (row box, column tile).
+//   3. nms_sweep_kernel  one CTA per segment walks the tiles in order: the diagonal word
+//                        chain is resolved serially, the kept rows' words are OR-reduced
+//                        into the running "removed" words by the whole CTA; then the kept
+//                        ORIGINAL indices are compacted in ascending order.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kTile = 64;
+constexpr int kSortThreads = 1024;
+constexpr int kSweepThreads = 512;
+constexpr int kMaxTiles = B200_NMS_MAX_SEG / kTile;  // 256
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ uint32_t desc_score_bits(float s) {
+  s = s + 0.0f;  // -0 -> +0 so both zeros tie
+  uint32_t u = __float_as_uint(s);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // ascending-orderable
+  return ~u;                                       // descending
+}
+
+// (x2 - x1 + 1) * (y2 - y1 + 1), three separately rounded ops per factor (nms_cpu.cpp:22)
+__device__ __forceinline__ float legacy_area(const float4 b) {
+  float w = __fadd_rn(__fsub_rn(b.z, b.x), 1.0f);
+  float h = __fadd_rn(__fsub_rn(b.w, b.y), 1.0f);
+  return __fmul_rn(w, h);
+}
+
+// nms_cpu.cpp:50-60 for one pair; `a` is the earlier-visited box.
+__device__ __forceinline__ bool suppresses(const float4 a, float area_a, const float4 b, float area_b,
+                                           float thresh) {
+  float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
+  float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+  float w = fmaxf(__fadd_rn(__fsub_rn(xx2, xx1), 1.0f), 0.0f);
+  float h = fmaxf(__fadd_rn(__fsub_rn(yy2, yy1), 1.0f), 0.0f);
+  float inter = __fmul_rn(w, h);
+  // 0/x is 0 or NaN: never >= a positive threshold, so the division can be skipped.
+  if (inter == 0.0f && thresh > 0.0f) return false;
+  float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+  return __fdiv_rn(inter, uni) >= thresh;
+}
+
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSortThreads)
+nms_sort_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores,
+                const int32_t* __restrict__ seg_off, int max_seg_len, float4* __restrict__ sboxes,
+                int32_t* __restrict__ order, int32_t* __restrict__ sorted_flag) {
+  extern __shared__ u64 keys[];
+  __shared__ int s_unsorted;
+  const int s = blockIdx.x, tid = threadIdx.x;
+  const int off = seg_off[s];
+  int n = seg_off[s + 1] - off;
+  if (n > max_seg_len) n = max_seg_len;
+  if (n <= 0) {
+    if (tid == 0) sorted_flag[s] = 1;
+    return;
+  }
+  int npad = 2;
+  while (npad < n) npad <<= 1;
+  if (tid == 0) s_unsorted = 0;
+  for (int i = tid; i < npad; i += kSortThreads)
+    keys[i] = i < n ? ((u64)desc_score_bits(scores[off + i]) << 32) | (uint32_t)i : ~0ull;
+  __syncthreads();
+  for (int i = tid; i + 1 < n; i += kSortThreads)
+    if (keys[i] > keys[i + 1]) s_unsorted = 1;
+  __syncthreads();
+  const bool unsorted = s_unsorted != 0;
+  if (unsorted) {
+    for (int k = 2; k <= npad; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int t = tid; t < (npad >> 1); t += kSortThreads) {
+          int lo = 2 * t - (t & (j - 1));
+          int hi = lo + j;
+          u64 a = keys[lo], b = keys[hi];
+          bool up = (lo & k) == 0;
+          if ((a > b) == up) {
+            keys[lo] = b;
+            keys[hi] = a;
+          }
+        }
+        __syncthreads();
+      }
+    }
+  }
+  for (int i = tid; i < n; i += kSortThreads) {
+    int src = (int)(uint32_t)keys[i];
+    order[off + i] = src;
+    sboxes[off + i] = boxes[off + src];
+  }
+  if (tid == 0) sorted_flag[s] = unsorted ? 0 : 1;
+}
+
+// ---------------------------------------------------------------------------------------
+// grid (S, MB, MB): blockIdx.y = row tile i, blockIdx.z = column tile j >= i.
+__global__ void __launch_bounds__(kTile)
+nms_mask_kernel(const float4* __restrict__ sboxes, const int32_t* __restrict__ seg_off, int max_seg_len,
+                int MB, float thresh, u64* __restrict__ mask) {
+  const int s = blockIdx.x, i = blockIdx.y, j = blockIdx.z;
+  if (j < i) return;
+  const int off = seg_off[s];
+  int n = seg_off[s + 1] - off;
+  if (n > max_seg_len) n = max_seg_len;
+  if (j * kTile >= n) return;
+  __shared__ float4 cbox[kTile];
+  __shared__ float carea[kTile];
+  const int t = threadIdx.x;
+  const int ncol = min(kTile, n - j * kTile);
+  if (t < ncol) {
+    float4 b = sboxes[off + j * kTile + t];
+    cbox[t] = b;
+    carea[t] = legacy_area(b);
+  }
+  __syncthreads();
+  const int row = i * kTile + t;
+  if (row >= n) return;
+  const float4 a = sboxes[off + row];
+  const float area_a = legacy_area(a);
+  u64 bits = 0;
+  for (int c = (i == j) ? t + 1 : 0; c < ncol; ++c)
+    if (suppresses(a, area_a, cbox[c], carea[c], thresh)) bits |= 1ull << c;
+  mask[(size_t)(off + row) * MB + j] = bits;
+}
+
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSweepThreads)
+nms_sweep_kernel(const u64* __restrict__ mask, const int32_t* __restrict__ order,
+                 const int32_t* __restrict__ sorted_flag, const int32_t* __restrict__ seg_off,
+                 int max_seg_len, int MB, long long max_keep, long long* __restrict__ keep_idx,
+                 int32_t* __restrict__ keep_cnt) {
+  __shared__ u64 remv[kMaxTiles];      // bit set = sorted position already suppressed
+  __shared__ u64 keepbits[kMaxTiles];  // bit set = ORIGINAL index kept
+  __shared__ u64 diag[2][kTile];
+  __shared__ int scan[kMaxTiles];
+  __shared__ u64 s_kept;
+  __shared__ int s_nkept;
+  const int s = blockIdx.x, tid = threadIdx.x;
+  const int off = seg_off[s];
+  int n = seg_off[s + 1] - off;
+  if (n > max_seg_len) n = max_seg_len;
+  if (n <= 0) {
+    if (tid == 0) keep_cnt[s] = 0;
+    return;
+  }
+  const int nb = (n + kTile - 1) / kTile;
+  for (int w = tid; w < kMaxTiles; w += kSweepThreads) {
+    remv[w] = 0;
+    keepbits[w] = 0;
+  }
+  if (tid < kTile) diag[0][tid] = tid < n ? mask[(size_t)(off + tid) * MB] : 0;
+  if (tid == 0) s_nkept = 0;
+  const bool can_stop = max_keep > 0 && sorted_flag[s] != 0;
+  __syncthreads();
+
+  for (int i = 0; i < nb; ++i) {
+    const int cur = i & 1;
+    if (tid == 0) {
+      // serial resolve of tile i: a row survives if no earlier kept row removed it
+      u64 gone = remv[i], kept = 0;
+      const int nrows = min(kTile, n - i * kTile);
+#pragma unroll 8
+      for (int r = 0; r < nrows; ++r) {
+        u64 d = diag[cur][r];
+        if (!((gone >> r) & 1ull)) {
+          kept |= 1ull << r;
+          gone |= d;
+        }
+      }
+      s_kept = kept;
+      s_nkept += __popcll(kept);
+    } else if (tid >= 64 && tid < 64 + kTile && i + 1 < nb) {
+      // prefetch the next tile's diagonal words while thread 0 works
+      int row = (i + 1) * kTile + (tid - 64);
+      diag[cur ^ 1][tid - 64] = row < n ? mask[(size_t)(off + row) * MB + (i + 1)] : 0;
+    }
+    __syncthreads();
+    const u64 kept = s_kept;
+    if (tid < kTile && ((kept >> tid) & 1ull)) {
+      int o = order[off + i * kTile + tid];
+      atomicOr(&keepbits[o >> 6], 1ull << (o & 63));
+    }
+    if (can_stop && (long long)s_nkept >= max_keep) break;  // uniform: shared values
+    const int ncols = nb - (i + 1);
+    if (ncols > 0 && kept != 0) {
+      // OR the kept rows' words into remv[i+1 ..].  Thread (rg, jj) takes rows rg, rg+RG, ...
+      // of column word jj; the loads are independent of each other, so they are all issued
+      // before the first one is consumed (one memory round trip per tile, not one per row).
+      const int RG = kSweepThreads / ncols;  // >= 2 since ncols <= 255
+      const int rg = tid / ncols, jj = tid - rg * ncols;
+      if (rg < RG) {
+        const u64* base = mask + (size_t)(off + i * kTile) * MB + (i + 1) + jj;
+        u64 acc = 0;
+        for (int r0 = rg; r0 < kTile; r0 += 8 * RG) {
+          u64 v[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int r = r0 + k * RG;
+            v[k] = (r < kTile && ((kept >> r) & 1ull)) ? __ldg(base + (size_t)r * MB) : 0ull;
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc |= v[k];
+        }
+        if (acc) atomicOr(&remv[i + 1 + jj], acc);
+      }
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+
+  // ascending compaction of the kept original indices
+  const int nw = nb;  // original indices also span ceil(n/64) words
+  if (tid < kMaxTiles) scan[tid] = tid < nw ? __popcll(keepbits[tid]) : 0;
+  __syncthreads();
+  for (int d = 1; d < kMaxTiles; d <<= 1) {
+    int v = 0;
+    if (tid < kMaxTiles && tid >= d) v = scan[tid - d];
+    __syncthreads();
+    if (tid < kMaxTiles) scan[tid] += v;
+    __syncthreads();
+  }
+  const int total = scan[kMaxTiles - 1];
+  const int limit = (max_keep > 0 && max_keep < (long long)total) ? (int)max_keep : total;
+  if (tid < nw) {
+    u64 bits = keepbits[tid];
+    int pos = scan[tid] - __popcll(bits);
+    while (bits && pos < limit) {
+      int b = __ffsll((long long)bits) - 1;
+      bits &= bits - 1;
+      keep_idx[off + pos] = (long long)tid * 64 + b;
+      ++pos;
+    }
+  }
+  for (int p = limit + tid; p < n; p += kSweepThreads) keep_idx[off + p] = -1;
+  if (tid == 0) keep_cnt[s] = limit;
+}
+
+// ---------------------------------------------------------------------------------------
+// Fused single-kernel path (segments up to kFusedMaxSeg boxes): one CTA per segment keeps
+// the segment's boxes in shared memory and never materialises the N x N/64 bitmask.
+// Tiles of 64 boxes are visited in order; for tile i
+//   (a) the 64x64 diagonal IoU words are computed on the fly (rows already removed skip),
+//   (b) one thread resolves the in-tile chain,
+//   (c) every still-alive LATER box is tested only against the tile's KEPT boxes and the
+//       per-warp verdicts are merged with a ballot into the "removed" bit words.
+// Work is sum_i kept_i * alive_later_i pair tests instead of N^2/2, and stops as soon as
+// max_keep boxes are kept when the segment arrived sorted (RPN top-k output does).
+// ---------------------------------------------------------------------------------------
+constexpr int kFusedMaxSeg = 13952;  // 16 B * n of dynamic shared memory next to ~8 KB static
+
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads, 1)
+nms_fused_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores,
+                 const int32_t* __restrict__ seg_off, int max_seg_len, float thresh, long long max_keep,
+                 int32_t* __restrict__ order, long long* __restrict__ keep_idx, int32_t* __restrict__ keep_cnt) {
+  extern __shared__ __align__(16) unsigned char fused_smem[];
+  float4* sb = reinterpret_cast<float4*>(fused_smem);  // boxes in visiting order
+  u64* keys = reinterpret_cast<u64*>(fused_smem);      // aliases sb during the sort
+  __shared__ uint32_t remv[B200_NMS_MAX_SEG / 32];
+  __shared__ u64 keepbits[kMaxTiles];
+  __shared__ u64 diag[kTile];
+  __shared__ float4 kb[kTile];
+  __shared__ float ka[kTile];
+  __shared__ int scan[kMaxTiles];
+  __shared__ u64 s_kept;
+  __shared__ int s_nkept, s_unsorted;
+
+  const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  const int off = seg_off[s];
+  int n = seg_off[s + 1] - off;
+  if (n > max_seg_len) n = max_seg_len;
+  if (n <= 0) {
+    if (tid == 0) keep_cnt[s] = 0;
+    return;
+  }
+  const int nb = (n + kTile - 1) / kTile;
+
+  // ---- visiting order -------------------------------------------------------------------
+  if (tid == 0) {
+    s_unsorted = 0;
+    s_nkept = 0;
+  }
+  for (int w = tid; w < nb * 2; w += kThreads) remv[w] = 0;
+  for (int w = tid; w < nb; w += kThreads) keepbits[w] = 0;
+  __syncthreads();
+  for (int i = tid; i + 1 < n; i += kThreads) {
+    const u64 a = ((u64)desc_score_bits(scores[off + i]) << 32) | (uint32_t)i;
+    const u64 b = ((u64)desc_score_bits(scores[off + i + 1]) << 32) | (uint32_t)(i + 1);
+    if (a > b) s_unsorted = 1;
+  }
+  __syncthreads();
+  const bool unsorted = s_unsorted != 0;
+  if (unsorted) {
+    int npad = 2;
+    while (npad < n) npad <<= 1;
+    for (int i = tid; i < npad; i += kThreads)
+      keys[i] = i < n ? ((u64)desc_score_bits(scores[off + i]) << 32) | (uint32_t)i : ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= npad; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int t = tid; t < (npad >> 1); t += kThreads) {
+          const int lo = 2 * t - (t & (j - 1)), hi = lo + j;
+          const u64 a = keys[lo], b = keys[hi];
+          if ((a > b) == ((lo & k) == 0)) {
+            keys[lo] = b;
+            keys[hi] = a;
+          }
+        }
+        __syncthreads();
+      }
+    }
+    for (int i = tid; i < n; i += kThreads) order[off + i] = (int)(uint32_t)keys[i];
+    __syncthreads();  // keys are dead from here; the same bytes become sb
+    for (int i = tid; i < n; i += kThreads) sb[i] = boxes[off + order[off + i]];
+  } else {
+    for (int i = tid; i < n; i += kThreads) sb[i] = boxes[off + i];
+  }
+  const bool can_stop = max_keep > 0 && !unsorted;
+  __syncthreads();
+
+  constexpr int G = kThreads / kTile;  // threads cooperating on one diagonal row
+  constexpr int CPT = kTile / G;       // columns per thread
+  for (int i = 0; i < nb; ++i) {
+    const int base = i * kTile;
+    const int nrows = min(kTile, n - base);
+    const u64 gone0 = ((u64)remv[2 * i + 1] << 32) | remv[2 * i];
+    const u64 live_mask = nrows == 64 ? ~0ull : ((1ull << nrows) - 1);
+    if ((gone0 & live_mask) == live_mask) continue;  // whole tile already removed (uniform)
+
+    // (a) diagonal words: thread (row r, column group cg) tests CPT columns > r
+    {
+      const int r = tid / G, cg = tid % G;
+      u64 bits = 0;
+      if (r < nrows && !((gone0 >> r) & 1ull)) {
+        const float4 a = sb[base + r];
+        const float area_a = legacy_area(a);
+#pragma unroll 4
+        for (int k = 0; k < CPT; ++k) {
+          const int c = cg * CPT + k;
+          if (c > r && c < nrows) {
+            const float4 b = sb[base + c];
+            if (suppresses(a, area_a, b, legacy_area(b), thresh)) bits |= 1ull << c;
+          }
+        }
+      }
+#pragma unroll
+      for (int d = G / 2; d > 0; d >>= 1) bits |= __shfl_xor_sync(0xffffffffu, bits, d);
+      if (cg == 0) diag[r] = bits;
+    }
+    __syncthreads();
+    // (b) in-tile chain
+    if (tid == 0) {
+      u64 gone = gone0, kept = 0;
+#pragma unroll 8
+      for (int r = 0; r < nrows; ++r) {
+        const u64 d = diag[r];
+        if (!((gone >> r) & 1ull)) {
+          kept |= 1ull << r;
+          gone |= d;
+        }
+      }
+      s_kept = kept;
+      s_nkept += __popcll(kept);
+    }
+    __syncthreads();
+    const u64 kept = s_kept;
+    const int m = __popcll(kept);
+    if (tid < kTile && ((kept >> tid) & 1ull)) {
+      const int pos = __popcll(kept & ((1ull << tid) - 1));
+      const float4 b = sb[base + tid];
+      kb[pos] = b;
+      ka[pos] = legacy_area(b);
+      const int o = unsorted ? order[off + base + tid] : base + tid;
+      atomicOr(&keepbits[o >> 6], 1ull << (o & 63));
+    }
+    if (can_stop && (long long)s_nkept >= max_keep) break;  // uniform: shared value
+    __syncthreads();
+    // (c) later boxes vs this tile's kept boxes
+    for (int j0 = base + kTile + (tid & ~31); j0 < n; j0 += kThreads) {
+      const int j = j0 + lane;
+      const uint32_t dead = remv[j0 >> 5];
+      bool sup = false;
+      if (j < n && !((dead >> lane) & 1u)) {
+        const float4 b = sb[j];
+        const float area_b = legacy_area(b);
+        for (int r = 0; r < m; ++r)
+          if (suppresses(kb[r], ka[r], b, area_b, thresh)) {
+            sup = true;
+            break;
+          }
+      }
+      const uint32_t v = __ballot_sync(0xffffffffu, sup);
+      if (lane == 0 && v) remv[j0 >> 5] = dead | v;
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+
+  // ---- ascending compaction of the kept original indices --------------------------------
+  for (int w = tid; w < kMaxTiles; w += kThreads) scan[w] = w < nb ? __popcll(keepbits[w]) : 0;
+  __syncthreads();
+  for (int d = 1; d < kMaxTiles; d <<= 1) {
+    int v[(kMaxTiles + kThreads - 1) / kThreads];
+    int k = 0;
+    for (int w = tid; w < kMaxTiles; w += kThreads) v[k++] = w >= d ? scan[w - d] : 0;
+    __syncthreads();
+    k = 0;
+    for (int w = tid; w < kMaxTiles; w += kThreads) scan[w] += v[k++];
+    __syncthreads();
+  }
+  const int total = scan[kMaxTiles - 1];
+  const int limit = (max_keep > 0 && max_keep < (long long)total) ? (int)max_keep : total;
+  for (int w = tid; w < nb; w += kThreads) {
+    u64 bits = keepbits[w];
+    int pos = scan[w] - __popcll(bits);
+    while (bits && pos < limit) {
+      const int b = __ffsll((long long)bits) - 1;
+      bits &= bits - 1;
+      keep_idx[off + pos] = (long long)w * 64 + b;
+      ++pos;
+    }
+  }
+  for (int p = limit + tid; p < n; p += kThreads) keep_idx[off + p] = -1;
+  if (tid == 0) keep_cnt[s] = limit;
+}
+
+bool g_nms_force_bitmask = false;
+
+struct Workspace {
+  float4* sboxes;
+  int32_t* order;
+  int32_t* sorted_flag;
+  u64* mask;
+  size_t bytes;
+};
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+Workspace carve(void* base, int64_t n_total, int64_t n_segments, int64_t max_seg_len) {
+  Workspace w;
+  size_t MB = (size_t)b200::ceil_div<int64_t>(max_seg_len > 0 ? max_seg_len : 1, kTile);
+  size_t o = 0;
+  char* p = static_cast<char*>(base);
+  w.sboxes = reinterpret_cast<float4*>(p + o);
+  o = align_up(o + sizeof(float4) * (size_t)n_total, 256);
+  w.order = reinterpret_cast<int32_t*>(p + o);
+  o = align_up(o + sizeof(int32_t) * (size_t)n_total, 256);
+  w.sorted_flag = reinterpret_cast<int32_t*>(p + o);
+  o = align_up(o + sizeof(int32_t) * (size_t)n_segments, 256);
+  w.mask = reinterpret_cast<u64*>(p + o);
+  // the bitmask exists only on the three-kernel path
+  if (max_seg_len > kFusedMaxSeg || g_nms_force_bitmask) o = align_up(o + sizeof(u64) * (size_t)n_total * MB, 256);
+  w.bytes = o;
+  return w;
+}
+
+}  // namespace
+
+extern "C" void b200_debug_nms(int force_bitmask) { g_nms_force_bitmask = force_bitmask != 0; }
+
+extern "C" size_t b200_nms_workspace_bytes(int64_t n_total, int64_t n_segments, int64_t max_seg_len) {
+  if (n_total < 0 || n_segments < 0 || max_seg_len < 0) return 0;
+  return carve(nullptr, n_total, n_segments, max_seg_len).bytes;
+}
+
+extern "C" int b200_nms_batched(const float* boxes, const float* scores, const int32_t* seg_offsets,
+                                int64_t n_total, int64_t n_segments, int64_t max_seg_len, float thresh,
+                                int64_t max_keep, int64_t* keep_idx, int32_t* keep_cnt, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  using namespace b200;
+  B200_REQUIRE(n_total >= 0 && n_segments >= 0 && max_seg_len >= 0, "nms: negative size");
+  if (n_segments == 0) return B200_OK;
+  B200_REQUIRE(seg_offsets && keep_cnt, "nms: null seg_offsets / keep_cnt");
+  B200_REQUIRE(n_total == 0 || (boxes && scores && keep_idx && workspace), "nms: null pointer");
+  B200_REQUIRE(n_total == 0 || aligned16(boxes), "nms: boxes must be 16-byte aligned");
+  if (max_seg_len > B200_NMS_MAX_SEG) {
+    set_error("nms: max_seg_len %lld exceeds B200_NMS_MAX_SEG (%d)", (long long)max_seg_len, B200_NMS_MAX_SEG);
+    return B200_ERR_UNSUPPORTED;
+  }
+  B200_REQUIRE(n_total < (int64_t)1 << 31, "nms: n_total must fit int32");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (max_seg_len == 0) max_seg_len = 1;
+  Workspace w = carve(workspace, n_total, n_segments, max_seg_len);
+  if (w.bytes > workspace_bytes) {
+    set_error("nms: workspace %zu bytes < required %zu", workspace_bytes, w.bytes);
+    return B200_ERR_WORKSPACE;
+  }
+  const int64_t kMaxGridX = 2147483647LL;
+  B200_REQUIRE(n_segments <= kMaxGridX, "nms: too many segments");
+  if (max_seg_len <= kFusedMaxSeg && !g_nms_force_bitmask) {
+    const size_t smem = sizeof(float4) * (size_t)ceil_div<int64_t>(max_seg_len, kTile) * kTile;
+    if (max_seg_len <= 1024) {
+      auto kern = nms_fused_kernel<256>;
+      int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                          "nms: cudaFuncSetAttribute");
+      if (rc != B200_OK) return rc;
+      kern<<<(unsigned)n_segments, 256, smem, st>>>(reinterpret_cast<const float4*>(boxes), scores, seg_offsets,
+                                                    (int)max_seg_len, thresh, (long long)max_keep, w.order,
+                                                    reinterpret_cast<long long*>(keep_idx), keep_cnt);
+    } else {
+      auto kern = nms_fused_kernel<1024>;
+      int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                          "nms: cudaFuncSetAttribute");
+      if (rc != B200_OK) return rc;
+      kern<<<(unsigned)n_segments, 1024, smem, st>>>(reinterpret_cast<const float4*>(boxes), scores, seg_offsets,
+                                                     (int)max_seg_len, thresh, (long long)max_keep, w.order,
+                                                     reinterpret_cast<long long*>(keep_idx), keep_cnt);
+    }
+    B200_CHECK_LAUNCH("nms_fused_kernel");
+    return B200_OK;
+  }
+  const int MB = (int)ceil_div<int64_t>(max_seg_len, kTile);
+  int npad = 2;
+  while (npad < max_seg_len) npad <<= 1;
+  const size_t sort_smem = sizeof(u64) * (size_t)npad;
+  static bool attr_set = false;
+  if (!attr_set) {
+    int rc = check_cuda(cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(sizeof(u64) * B200_NMS_MAX_SEG)),
+                        "nms: cudaFuncSetAttribute");
+    if (rc != B200_OK) return rc;
+    attr_set = true;
+  }
+  nms_sort_kernel<<<(unsigned)n_segments, kSortThreads, sort_smem, st>>>(
+      reinterpret_cast<const float4*>(boxes), scores, seg_offsets, (int)max_seg_len, w.sboxes, w.order,
+      w.sorted_flag);
+  B200_CHECK_LAUNCH("nms_sort_kernel");
+  nms_mask_kernel<<<dim3((unsigned)n_segments, MB, MB), kTile, 0, st>>>(w.sboxes, seg_offsets, (int)max_seg_len,
+                                                                        MB, thresh, w.mask);
+  B200_CHECK_LAUNCH("nms_mask_kernel");
+  nms_sweep_kernel<<<(unsigned)n_segments, kSweepThreads, 0, st>>>(
+      w.mask, w.order, w.sorted_flag, seg_offsets, (int)max_seg_len, MB, (long long)max_keep,
+      reinterpret_cast<long long*>(keep_idx), keep_cnt);
+  B200_CHECK_LAUNCH("nms_sweep_kernel");
+  return B200_OK;
+}

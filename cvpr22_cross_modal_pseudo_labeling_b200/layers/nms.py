@@ -1,0 +1,73 @@
+"""NMS entry points.  `nms` mirrors maskrcnn_benchmark.layers.nms (reference
+layers/nms.py:8 -> _C.nms, csrc/nms.h:10-28); `nms_batched` is the segmented form the
+post-processors use instead of one call per (image, level) / (image, class)."""
+import torch
+
+from .. import _ext
+
+_ws_cache = {}
+
+
+def _workspace(nbytes, device):
+    """Grow-only scratch buffer per device (torch caching allocator owns the memory)."""
+    buf = _ws_cache.get(device)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[device] = buf
+    return buf
+
+
+def nms_batched(boxes, scores, seg_offsets, thresh, max_keep=-1, max_seg_len=None):
+    """Greedy NMS over S independent segments in one call, no host sync.
+
+    boxes [N,4] fp32 xyxy, scores [N] fp32, seg_offsets [S+1] int32 (device) with
+    seg_offsets[0]=0, seg_offsets[S]=N.  `max_seg_len` is a host upper bound on
+    the longest segment (defaults to N).  Returns (keep_idx int64 [N], keep_cnt
+    int32 [S]): segment s's kept indices (local to the segment, ascending) sit at
+    keep_idx[seg_offsets[s] : seg_offsets[s] + keep_cnt[s]], the rest is -1.
+    """
+    _ext.require_cuda(boxes, "boxes")
+    _ext.require_cuda(scores, "scores")
+    _ext.require_cuda(seg_offsets, "seg_offsets")
+    if boxes.dim() != 2 or boxes.size(1) != 4:
+        raise ValueError("boxes must be [N,4]")
+    n = boxes.size(0)
+    if scores.numel() != n:
+        raise ValueError("scores must have one entry per box")
+    s = seg_offsets.numel() - 1
+    if s < 0:
+        raise ValueError("seg_offsets must have at least one entry")
+    boxes = boxes.float().contiguous()
+    scores = scores.float().contiguous()
+    seg_offsets = seg_offsets.to(torch.int32).contiguous()
+    if max_seg_len is None:
+        max_seg_len = n
+    keep_idx = torch.empty((n,), dtype=torch.int64, device=boxes.device)
+    keep_cnt = torch.empty((s,), dtype=torch.int32, device=boxes.device)
+    if s == 0:
+        return keep_idx, keep_cnt
+    lib = _ext.lib()
+    nbytes = lib.b200_nms_workspace_bytes(n, s, max_seg_len)
+    ws = _workspace(nbytes, boxes.device)
+    with torch.cuda.device(boxes.device):
+        rc = lib.b200_nms_batched(_ext.ptr(boxes), _ext.ptr(scores), _ext.ptr(seg_offsets), n, s,
+                                  int(max_seg_len), float(thresh), int(max_keep), _ext.ptr(keep_idx),
+                                  _ext.ptr(keep_cnt), _ext.ptr(ws), ws.numel(), _ext.stream_ptr(boxes.device))
+    _ext.check(rc, "b200_nms_batched")
+    return keep_idx, keep_cnt
+
+
+def nms(dets, scores, threshold):
+    """_C.nms(dets[N,4], scores[N], threshold) -> int64 keep indices, ascending
+    (reference csrc/cpu/nms_cpu.cpp:64).  Semantics of the CPU reference (`>=`,
+    +1 extents).  One host sync to size the result, as the reference's CUDA path
+    has (csrc/cuda/nms.cu:99-103)."""
+    _ext.require_cuda(dets, "dets")
+    _ext.require_cuda(scores, "scores")
+    if dets.numel() == 0:
+        # reference returns an empty int64 CPU tensor (csrc/nms.h:17-18); keep the device
+        return torch.empty((0,), dtype=torch.int64, device=dets.device)
+    n = dets.size(0)
+    off = torch.tensor([0, n], dtype=torch.int32, device=dets.device)
+    keep_idx, keep_cnt = nms_batched(dets, scores, off, threshold, -1, n)
+    return keep_idx[: int(keep_cnt.item())]

@@ -1,0 +1,207 @@
+/*
+ * b200det.h -- C ABI of the B200-native RoI hot path (libb200det.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.
+ * Every entry point names the reference interface it replaces
+ * (paths relative to /root/reference/maskrcnn_benchmark).  INTEGRATION.md shows
+ * the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - all data pointers are DEVICE pointers unless a parameter says "host";
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *     every kernel is launched on it and no call synchronises the host;
+ *   - nothing is allocated: the caller owns outputs and workspaces
+ *     (`*_workspace_bytes` tells how much);
+ *   - return value: B200_OK (0) or a negative b200_status; a human-readable
+ *     message for the calling thread's last failure is in b200_last_error_string();
+ *   - there is no CPU implementation behind any symbol.
+ */
+#ifndef B200DET_H_
+#define B200DET_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200DET_VERSION 100 /* major*1000 + minor*100 + patch */
+
+typedef enum {
+  B200_OK = 0,
+  B200_ERR_INVALID_ARG = -1, /* bad shape / null pointer / misaligned pointer */
+  B200_ERR_CUDA = -2,        /* a CUDA runtime / driver call failed          */
+  B200_ERR_WORKSPACE = -3,   /* workspace too small                          */
+  B200_ERR_UNSUPPORTED = -4  /* size or option outside what the kernels cover */
+} b200_status;
+
+int b200_version(void);
+const char* b200_last_error_string(void);
+
+/* ------------------------------------------------------------------------
+ * Feature layout of a level: logical shape is always [B, C, H, W] fp32.
+ *   B200_LAYOUT_NCHW : contiguous as the reference requires
+ *                      (csrc/cuda/ROIAlign_cuda.cu:286 `.contiguous()`).
+ *   B200_LAYOUT_NHWC : torch.channels_last strides (memory [B, H, W, C]); the
+ *                      fast path -- 128-bit channel-vector gathers staged in
+ *                      shared memory by bulk async copies.
+ * ------------------------------------------------------------------------ */
+#define B200_LAYOUT_NCHW 0
+#define B200_LAYOUT_NHWC 1
+#define B200_MAX_LEVELS 8
+
+typedef struct {
+  const float* data;   /* device, 16-byte aligned                           */
+  int32_t height;
+  int32_t width;
+  float spatial_scale; /* 1/stride of this level                            */
+} b200_level;
+
+typedef struct {
+  float* data; /* gradient buffer of a level, same layout as the forward input */
+  int32_t height;
+  int32_t width;
+  float spatial_scale;
+} b200_level_grad;
+
+/*
+ * Fused multi-level RoIAlign forward.
+ * Replaces, in one launch:  Pooler.forward  (modeling/poolers.py:91-121)
+ *   = convert_to_roi_format + LevelMapper (poolers.py:31-42) + per-level
+ *     _C.roi_align_forward (csrc/ROIAlign.h:11-24; kernels csrc/cpu/ROIAlign_cpu.cpp:221,
+ *     csrc/cuda/ROIAlign_cuda.cu:257) + the result[idx] = ... scatter.
+ * With n_levels == 1 it is exactly _C.roi_align_forward.
+ *
+ *   levels[n_levels]  host array; level l has scale spatial_scale[l]; for
+ *                     n_levels > 1 the FPN level of each RoI is
+ *                     floor(4 + log2(sqrt(area)/224 + 1e-6)) clamped to
+ *                     [-log2(scale[0]), -log2(scale[n-1])], evaluated op by op in fp32.
+ *   rois  [n_rois,5]  fp32 (batch_index, x1, y1, x2, y2) in image pixels
+ *   out   [n_rois, channels, pooled_h, pooled_w] fp32, contiguous (always NCHW order)
+ *   out_levels        optional int32 [n_rois]: the level each RoI used (may be NULL)
+ */
+int b200_roi_align_forward(const b200_level* levels, int n_levels, int layout,
+                           int batch, int channels, const float* rois,
+                           int64_t n_rois, int pooled_h, int pooled_w,
+                           int sampling_ratio, float* out, int32_t* out_levels,
+                           void* stream);
+
+/*
+ * Fused multi-level RoIAlign backward (gradient w.r.t. the features).
+ * Replaces _C.roi_align_backward (csrc/ROIAlign.h:27-45; kernel
+ * csrc/cuda/ROIAlign_cuda.cu:178-254, host :302-346) for every level at once.
+ * The level gradient buffers must be zero-filled by the caller (the reference
+ * allocates them with at::zeros, ROIAlign_cuda.cu:316); contributions are
+ * ADDED, so one buffer can collect several calls.
+ *   grad_out [n_rois, channels, pooled_h, pooled_w] fp32 contiguous
+ */
+int b200_roi_align_backward(const b200_level_grad* levels, int n_levels,
+                            int layout, int batch, int channels,
+                            const float* rois, int64_t n_rois, int pooled_h,
+                            int pooled_w, int sampling_ratio,
+                            const float* grad_out, void* stream);
+
+/*
+ * NCHW -> NHWC staging copy of one level ([B,C,H,W] contiguous -> [B,H,W,C]).
+ * No reference counterpart: it is what a caller uses when its backbone emits
+ * NCHW-contiguous maps and it wants the NHWC fast path ("layouts").
+ */
+int b200_nchw_to_nhwc(const float* src, float* dst, int batch, int channels,
+                      int height, int width, void* stream);
+int b200_nhwc_to_nchw(const float* src, float* dst, int batch, int channels,
+                      int height, int width, void* stream);
+
+/*
+ * Batched (segmented) greedy NMS.
+ * Replaces _C.nms (csrc/nms.h:10-28 -> csrc/cpu/nms_cpu.cpp:67, csrc/cuda/nms.cu:70)
+ * and the Python loops that call it once per (image, level) and per
+ * (image, class): modeling/rpn/inference.py:111-122,
+ * modeling/roi_heads/box_head/inference.py:135-149,
+ * structures/boxlist_ops.py:9-31.
+ * Semantics are the CPU reference's: legacy +1 widths, suppress when
+ * IoU >= thresh, fp32 with separately rounded operations; visiting order is
+ * descending score, equal scores visited in ascending index order.
+ *
+ *   boxes  [n_total,4] fp32 xyxy        scores [n_total] fp32
+ *   seg_offsets [n_segments+1] int32 device, ascending, seg_offsets[0] == 0 and
+ *               seg_offsets[n_segments] == n_total; segment s owns
+ *               boxes[seg_offsets[s] : seg_offsets[s+1]]
+ *   max_seg_len host upper bound on any segment's length (sizes grids and the
+ *               workspace; <= B200_NMS_MAX_SEG)
+ *   max_keep    > 0: only the first max_keep kept indices (ascending index
+ *               order, as boxlist_nms's keep[:max_proposals]) are reported
+ *   keep_idx [n_total] int64: for segment s the kept indices, LOCAL to the
+ *               segment, ascending, at keep_idx[seg_offsets[s] ...]; the rest
+ *               of the segment's slots are set to -1
+ *   keep_cnt [n_segments] int32: number of kept entries per segment
+ */
+#define B200_NMS_MAX_SEG 16384
+size_t b200_nms_workspace_bytes(int64_t n_total, int64_t n_segments,
+                                int64_t max_seg_len);
+int b200_nms_batched(const float* boxes, const float* scores,
+                     const int32_t* seg_offsets, int64_t n_total,
+                     int64_t n_segments, int64_t max_seg_len, float thresh,
+                     int64_t max_keep, int64_t* keep_idx, int32_t* keep_cnt,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Region -> class-embedding scoring: logits = A . E^T on the tcgen05 tensor
+ * cores (bf16 operands, fp32 accumulation in TMEM) with the consumer fused
+ * into the epilogue.  Replaces
+ *   roi_box_predictors.py:67   einsum('pe,ce->pc', cls_emb, cls_score)
+ *   box_head/inference.py:62   F.softmax(class_logits, -1)  (+ the `> score_thresh`
+ *                              candidate test of :134)
+ *   detector/st_generalized_rcnn.py:245-255  einsum('pd,wd->pw') + max over
+ *                              regions + sigmoid (caption alignment)
+ *
+ *   A [n_rows, dim] bf16 row-major (projected RoI embeddings), 16-byte aligned,
+ *     dim % 8 == 0;  E [n_cols, dim] bf16 row-major (class / word embeddings).
+ *
+ * B200_MATCH_SOFTMAX (n_cols <= 512):
+ *   probs  [n_rows, n_cols] fp32  row softmax (may be NULL)
+ *   logits [n_rows, n_cols] fp32  raw scores  (may be NULL)
+ *   top_label [n_rows] int32 / top_prob [n_rows] fp32: arg-max over columns
+ *     >= 1 (column 0 is the background row) and its probability; top_label is
+ *     0 when that probability is <= score_thresh (may be NULL)
+ * B200_MATCH_COLMAX:
+ *   row_seg [n_rows] int32 : image index of each row (ascending)
+ *   col_seg [n_cols] int32 : image index of each column (word)
+ *   col_best [n_cols] uint64, caller-initialised to 0: receives per column the
+ *     packed maximum over the rows of ITS image,
+ *       (orderable(score) << 32) | (0xFFFFFFFF - local_row)
+ *     so equal scores resolve to the first row, as torch.max does
+ *     (decode with b200_colmax_decode).
+ *   logits may be non-NULL to also get the raw [n_rows, n_cols] scores.
+ */
+#define B200_MATCH_SOFTMAX 0
+#define B200_MATCH_COLMAX 1
+int b200_embed_match(const void* A_bf16, const void* E_bf16, int64_t n_rows,
+                     int n_cols, int dim, int mode, float score_thresh,
+                     float* probs, float* logits, int32_t* top_label,
+                     float* top_prob, const int32_t* row_seg,
+                     const int32_t* col_seg, const int32_t* row_seg_start,
+                     uint64_t* col_best, void* stream);
+/* col_best -> (row index local to the image, max score, sigmoid(max score)) */
+int b200_colmax_decode(const uint64_t* col_best, int n_cols, int32_t* row_idx,
+                       float* max_score, float* sigmoid_score, void* stream);
+
+/*
+ * RoIPool (max) forward / backward -- API compatibility with
+ * _C.roi_pool_forward / _C.roi_pool_backward (csrc/ROIPool.h:11-48, kernels
+ * csrc/cuda/ROIPool_cuda.cu:17-108).  NCHW only; no model in the reference uses it.
+ */
+int b200_roi_pool_forward(const float* input, int batch, int channels,
+                          int height, int width, const float* rois,
+                          int64_t n_rois, float spatial_scale, int pooled_h,
+                          int pooled_w, float* out, int32_t* argmax,
+                          void* stream);
+int b200_roi_pool_backward(const float* grad_out, const int32_t* argmax,
+                           const float* rois, int64_t n_rois, int batch,
+                           int channels, int height, int width, int pooled_h,
+                           int pooled_w, float* grad_in, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200DET_H_ */

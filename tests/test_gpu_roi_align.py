@@ -1,0 +1,196 @@
+"""GPU parity: RoIAlign forward/backward, fused multi-level Pooler, layouts, RoIPool -- through
+the C ABI, against the CPU oracle.  Forward tolerance: bit-exact in the default (exact)
+mode; rtol 1e-5 (+ atol 1e-6) in the FMA mode.  Backward: rtol 1e-5 of the fp64-accumulated
+oracle, scaled per element by the sum of |addends| (atomics reorder fp32 sums)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def _ext():
+    from cvpr22_cross_modal_pseudo_labeling_b200 import _ext
+    return _ext
+
+
+def _feat(rng, b, c, h, w, nhwc):
+    x = torch.from_numpy(rng.standard_normal((b, c, h, w)).astype(np.float32)).cuda()
+    return x.contiguous(memory_format=torch.channels_last) if nhwc else x
+
+
+def _rand_rois(rng, n, b, img_w, img_h):
+    return synth.make_rois(rng, n, b, img_w, img_h, smin=4.0, smax=float(max(img_w, img_h)))
+
+
+CASES = [
+    # (B, C, H, W, scale, PH, PW, sr, n_rois)
+    (2, 64, 50, 84, 1 / 16, 7, 7, 2, 60),
+    (2, 128, 25, 42, 1 / 32, 14, 14, 2, 40),
+    (1, 64, 100, 168, 1 / 8, 7, 7, 2, 80),
+    (1, 32, 50, 84, 1 / 16, 14, 14, 0, 50),   # C4-style adaptive sampling (config #1 shape, fewer channels)
+    (2, 16, 30, 40, 1 / 16, 3, 5, 3, 30),
+    (1, 8, 20, 20, 1 / 4, 1, 1, 1, 10),
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("nhwc", [False, True])
+def test_roi_align_forward_exact(case, nhwc):
+    from cvpr22_cross_modal_pseudo_labeling_b200.layers import roi_align
+    b, c, h, w, scale, ph, pw, sr, n = case
+    rng = np.random.default_rng(hash(case) % 2**31)
+    x = _feat(rng, b, c, h, w, nhwc)
+    rois = _rand_rois(rng, n, b, int(w / scale), int(h / scale))
+    rois[:3, 3] = rois[:3, 1] - 7           # malformed (x2 < x1): forced to 1x1 (ROIAlign_cpu.cpp:156)
+    rois[3:6, 1:] += 5000                   # fully outside: zeros (ROIAlign_cpu.cpp:47)
+    want = oracle.roi_align_forward(x.cpu().contiguous().numpy(), rois, scale, ph, pw, sr)
+    _ext().debug_set(False, True, 0)
+    got = roi_align(x, torch.from_numpy(rois).cuda(), (ph, pw), scale, sr)
+    assert got.is_contiguous() and got.shape == want.shape
+    assert np.array_equal(got.cpu().numpy(), want)
+    assert np.all(want[3:6] == 0)
+    # generic kernel must agree with the staged one too
+    _ext().debug_set(True, True, 0)
+    got2 = roi_align(x, torch.from_numpy(rois).cuda(), (ph, pw), scale, sr)
+    _ext().debug_set(False, True, 0)
+    assert np.array_equal(got2.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("res", [7, 14])
+def test_roi_align_forward_occupancy_variants(variant, res):
+    """Every register/occupancy variant of the marching kernel must stay bit-exact."""
+    from cvpr22_cross_modal_pseudo_labeling_b200.layers import roi_align
+    rng = np.random.default_rng(variant)
+    x = _feat(rng, 2, 128, 50, 84, True)
+    rois = _rand_rois(rng, 100, 2, 1333, 800)
+    want = oracle.roi_align_forward(x.cpu().contiguous().numpy(), rois, 1 / 16, res, res, 2)
+    _ext().debug_set(False, True, variant)
+    got = roi_align(x, torch.from_numpy(rois).cuda(), (res, res), 1 / 16, 2)
+    _ext().debug_set(False, True, 0)
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_roi_align_forward_fma_mode_tolerance():
+    from cvpr22_cross_modal_pseudo_labeling_b200.layers import roi_align
+    rng = np.random.default_rng(3)
+    x = _feat(rng, 2, 64, 50, 84, True)
+    rois = _rand_rois(rng, 200, 2, 1333, 800)
+    want = oracle.roi_align_forward(x.cpu().contiguous().numpy(), rois, 1 / 16, 7, 7, 2)
+    _ext().debug_set(False, False, 0)
+    got = roi_align(x, torch.from_numpy(rois).cuda(), (7, 7), 1 / 16, 2).cpu().numpy()
+    _ext().debug_set(False, True, 0)
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=1e-6)
+
+
+def test_roi_align_known_answers():
+    from cvpr22_cross_modal_pseudo_labeling_b200.layers import roi_align
+    x = torch.arange(2 * 6 * 6, dtype=torch.float32, device="cuda").reshape(1, 2, 6, 6)
+    # RoI covering exactly pixel (y=2,x=3) cell centre: samples all inside one bilinear cell of a linear ramp
+    rois = torch.tensor([[0, 3.0, 2.0, 4.0, 3.0]], device="cuda")
+    out = roi_align(x, rois, (1, 1), 1.0, 2)
+    # ramp is linear -> average of samples = value at the RoI centre (3.5, 2.5)
+    assert torch.allclose(out[0, :, 0, 0].cpu(), torch.tensor([2.5 * 6 + 3.5, 36 + 2.5 * 6 + 3.5]))
+    e = roi_align(x, torch.zeros((0, 5), device="cuda"), (7, 7), 1.0, 2)
+    assert e.shape == (0, 2, 7, 7)
+    with pytest.raises(RuntimeError):
+        roi_align(x.cpu(), rois.cpu(), (1, 1), 1.0, 2)
+
+
+def _pyramid(rng, b, c, nhwc, img_h=800, img_w=1333):
+    shapes = synth.fpn_shapes(img_h, img_w)
+    return [_feat(rng, b, c, h, w, nhwc) for (h, w) in shapes]
+
+
+@pytest.mark.parametrize("nhwc", [False, True])
+@pytest.mark.parametrize("res", [7, 14])
+def test_pooler_multilevel_matches_oracle(nhwc, res):
+    from cvpr22_cross_modal_pseudo_labeling_b200.modeling import Pooler
+    from cvpr22_cross_modal_pseudo_labeling_b200.structures import BoxList
+    from cvpr22_cross_modal_pseudo_labeling_b200.layers.roi_align import _forward
+    rng = np.random.default_rng(17 + res)
+    b, c, n = 2, 64, 150
+    feats = _pyramid(rng, b, c, nhwc)
+    rois = synth.make_rois(rng, n, b)
+    boxes = [BoxList(torch.from_numpy(rois[i * n:(i + 1) * n, 1:]).cuda(), (synth.IMG_W, synth.IMG_H)) for i in range(b)]
+    pooler = Pooler((res, res), synth.FPN_SCALES, 2)
+    got = pooler(feats, boxes)
+    want, want_lv = oracle.pooler_forward([f.cpu().contiguous().numpy() for f in feats], rois, synth.FPN_SCALES, res, res, 2)
+    _, lv = _forward(feats, synth.FPN_SCALES, torch.from_numpy(rois).cuda(), (res, res), 2, want_levels=True)
+    lv = lv.cpu().numpy()
+    mism = int((lv != want_lv).sum())
+    assert mism == 0, "level mismatches: %d" % mism     # reported separately from value parity
+    assert len(np.unique(want_lv)) == 4                  # all four levels populated
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("nhwc", [False, True])
+@pytest.mark.parametrize("cfg", [(7, 7, 2), (14, 14, 2), (5, 3, 0)])
+def test_roi_align_backward(nhwc, cfg):
+    from cvpr22_cross_modal_pseudo_labeling_b200.layers import roi_align
+    ph, pw, sr = cfg
+    rng = np.random.default_rng(23 + ph)
+    b, c, h, w, scale, n = 2, 64, 25, 42, 1 / 32, 120
+    x = _feat(rng, b, c, h, w, nhwc).requires_grad_(True)
+    rois = _rand_rois(rng, n, b, 1333, 800)
+    g = rng.standard_normal((n * b, c, ph, pw)).astype(np.float32)
+    out = roi_align(x, torch.from_numpy(rois).cuda(), (ph, pw), scale, sr)
+    out.backward(torch.from_numpy(g).cuda())
+    got = x.grad.cpu().contiguous().numpy().astype(np.float64)
+    _, want64 = oracle.roi_align_backward(g, rois, scale, ph, pw, b, c, h, w, sr)
+    _, mag = oracle.roi_align_backward(np.abs(g), rois, scale, ph, pw, b, c, h, w, sr)   # sum of |addends|
+    err = np.abs(got - want64)
+    assert np.all(err <= RTOL * mag + 1e-30), float((err / (mag + 1e-30)).max())
+    assert (want64 != 0).any()
+
+
+def test_pooler_backward_multilevel():
+    from cvpr22_cross_modal_pseudo_labeling_b200.modeling import Pooler
+    from cvpr22_cross_modal_pseudo_labeling_b200.structures import BoxList
+    rng = np.random.default_rng(29)
+    b, c, n = 1, 64, 200
+    feats = [f.requires_grad_(True) for f in _pyramid(rng, b, c, True, 400, 672)]
+    rois = synth.make_rois(rng, n, b, 672, 400, smin=8, smax=400)
+    boxes = [BoxList(torch.from_numpy(rois[:, 1:]).cuda(), (672, 400))]
+    pooler = Pooler((7, 7), synth.FPN_SCALES, 2)
+    out = pooler(feats, boxes)
+    g = rng.standard_normal(tuple(out.shape)).astype(np.float32)
+    out.backward(torch.from_numpy(g).cuda())
+    lv = oracle.level_map(rois, 2.0, 5.0)
+    for l, f in enumerate(feats):
+        idx = np.nonzero(lv == l)[0]
+        _, want = oracle.roi_align_backward(g[idx], rois[idx], synth.FPN_SCALES[l], 7, 7, b, c, f.shape[2], f.shape[3], 2)
+        _, mag = oracle.roi_align_backward(np.abs(g[idx]), rois[idx], synth.FPN_SCALES[l], 7, 7, b, c, f.shape[2], f.shape[3], 2)
+        err = np.abs(f.grad.cpu().contiguous().numpy() - want)
+        assert np.all(err <= RTOL * mag + 1e-30), l
+
+
+def test_layout_roundtrip():
+    e = _ext()
+    x = torch.randn(3, 70, 37, 53, device="cuda")
+    y = torch.empty_like(x).contiguous(memory_format=torch.channels_last)
+    e.check(e.lib().b200_nchw_to_nhwc(e.ptr(x), e.ptr(y), 3, 70, 37, 53, e.stream_ptr()), "to_nhwc")
+    assert torch.equal(y, x)  # logical equality: y is channels_last memory
+    z = torch.empty_like(x)
+    e.check(e.lib().b200_nhwc_to_nchw(e.ptr(y), e.ptr(z), 3, 70, 37, 53, e.stream_ptr()), "to_nchw")
+    assert torch.equal(z, x)
+
+
+def test_roi_pool_matches_oracle():
+    from cvpr22_cross_modal_pseudo_labeling_b200.layers import ROIPool
+    rng = np.random.default_rng(31)
+    x = _feat(rng, 2, 16, 30, 40, False).requires_grad_(True)
+    rois = _rand_rois(rng, 50, 2, 640, 480)
+    out = ROIPool((7, 7), 1 / 16)(x, torch.from_numpy(rois).cuda())
+    want, arg = oracle.roi_pool_forward(x.detach().cpu().numpy(), rois, 1 / 16, 7, 7)
+    assert np.array_equal(out.detach().cpu().numpy(), want)
+    g = rng.standard_normal(want.shape).astype(np.float32)
+    out.backward(torch.from_numpy(g).cuda())
+    wg = oracle.roi_pool_backward(g, arg, rois, 7, 7, 2, 16, 30, 40)
+    np.testing.assert_allclose(x.grad.cpu().numpy(), wg, rtol=1e-5, atol=1e-6)
