@@ -1,0 +1,113 @@
+"""GPU parity: tcgen05 embedding-match kernel vs the oracle's fp64 restatement on the SAME
+bf16-rounded inputs.  Tolerances from BASELINE.json: class scores <= 2e-2 abs,
+top-1 pseudo-label agreement >= 99.9 %."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+ATOL = 2e-2
+
+
+def _inputs(seed, r, c, d, scale=3.0):
+    g = torch.Generator().manual_seed(seed)
+    A = (torch.randn((r, d), generator=g) * scale).to(torch.bfloat16)
+    E = torch.nn.functional.normalize(torch.randn((c, d), generator=g), dim=-1)
+    E[0] = 0  # background row (reference data/datasets/coco.py:85-89)
+    return A, E.to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("shape", [(1000, 66, 768), (300, 49, 768), (4096, 501, 512), (130, 18, 768),
+                                   (257, 1, 64), (5, 2, 8), (1000, 257, 200), (128, 512, 1024)])
+def test_softmax_mode(shape):
+    from cvpr22_cross_modal_pseudo_labeling_b200.layers import embed_match_softmax
+    r, c, d = shape
+    A, E = _inputs(sum(shape), r, c, d)
+    out = embed_match_softmax(A.cuda(), E.cuda(), 0.05, want_probs=True, want_logits=True)
+    An, En = A.float().numpy(), E.float().numpy()
+    probs, top, top_p, _ = oracle.embed_match_softmax(An, En, 0.05)
+    logits = oracle.embed_logits(An, En, np.float64)
+    np.testing.assert_allclose(out["logits"].cpu().numpy(), logits, atol=2e-3 * max(1.0, np.abs(logits).max()), rtol=0)
+    np.testing.assert_allclose(out["probs"].cpu().numpy(), probs, atol=ATOL, rtol=0)
+    assert np.abs(out["probs"].cpu().numpy().sum(1) - 1).max() < 1e-4
+    if c > 1:
+        # argmax over foreground columns, independent of the threshold
+        got_top = out["logits"][:, 1:].argmax(1).cpu().numpy() + 1
+        assert (got_top == top).mean() >= 0.999
+        lab = out["top_label"].cpu().numpy()
+        want_lab = np.where(top_p > 0.05, top, 0)
+        # labels may only differ where the top probability sits within tolerance of the threshold
+        bad = (lab != want_lab) & (np.abs(top_p - 0.05) > 1e-3) & (got_top == top)
+        assert not bad.any()
+        np.testing.assert_allclose(out["top_prob"].cpu().numpy(), top_p, atol=ATOL, rtol=0)
+
+
+def test_caption_align_matches_oracle():
+    from cvpr22_cross_modal_pseudo_labeling_b200.layers import caption_align
+    g = torch.Generator().manual_seed(5)
+    rows = [1000, 1000, 37, 0, 1000, 200]
+    words = [8, 0, 3, 2, 16, 1]
+    d = 768
+    emb = (torch.randn((sum(rows), d), generator=g) * 2).to(torch.bfloat16)
+    W = [torch.nn.functional.normalize(torch.randn((w, d), generator=g), dim=-1).to(torch.bfloat16) for w in words]
+    res = caption_align(emb.cuda(), rows, [w.cuda() for w in W])
+    o = 0
+    for i, (n, w) in enumerate(zip(rows, words)):
+        idx, mx, sg = [t.cpu().numpy() for t in res[i]]
+        assert len(idx) == w
+        if n and w:
+            widx, wmx, wsg = oracle.caption_align(emb[o:o + n].float().numpy(), W[i].float().numpy())
+            assert (idx == widx).mean() >= 0.999
+            np.testing.assert_allclose(mx, wmx, atol=2e-3 * max(1.0, np.abs(wmx).max()))
+            np.testing.assert_allclose(sg, wsg, atol=ATOL)
+        elif w:
+            assert (idx == -1).all()
+        o += n
+
+
+def test_caption_align_many_words_groups():
+    """More than 512 words in the batch: images are processed in column groups."""
+    from cvpr22_cross_modal_pseudo_labeling_b200.layers import caption_align
+    g = torch.Generator().manual_seed(6)
+    rows = [128] * 40
+    words = [16] * 40          # 640 words
+    d = 64
+    emb = torch.randn((sum(rows), d), generator=g).to(torch.bfloat16)
+    W = [torch.randn((w, d), generator=g).to(torch.bfloat16) for w in words]
+    res = caption_align(emb.cuda(), rows, [w.cuda() for w in W])
+    for i in (0, 31, 32, 39):
+        widx, _, _ = oracle.caption_align(emb[i * 128:(i + 1) * 128].float().numpy(), W[i].float().numpy())
+        assert (res[i][0].cpu().numpy() == widx).all()
+
+
+def test_ties_resolve_to_first_region():
+    from cvpr22_cross_modal_pseudo_labeling_b200.layers import caption_align
+    emb = torch.zeros((300, 64), dtype=torch.bfloat16)
+    emb[[7, 150, 299]] = 1.0          # three identical best regions
+    W = [torch.ones((2, 64), dtype=torch.bfloat16)]
+    idx, mx, _ = caption_align(emb.cuda(), [300], [W[0].cuda()])[0]
+    assert idx.tolist() == [7, 7] and mx.tolist() == [64.0, 64.0]   # torch.max returns the first index
+
+
+def test_embed_logits_autograd():
+    from cvpr22_cross_modal_pseudo_labeling_b200.layers import embed_logits
+    A, E = _inputs(9, 256, 49, 768, scale=1.0)
+    a = A.float().cuda().requires_grad_(True)
+    out = embed_logits(a, E.cuda())
+    w = torch.randn_like(out)
+    (out * w).sum().backward()
+    ref = (w @ E.float().cuda())
+    assert torch.allclose(a.grad, ref, atol=1e-4, rtol=1e-4)
+
+
+def test_bad_arguments():
+    from cvpr22_cross_modal_pseudo_labeling_b200.layers import embed_match_softmax
+    with pytest.raises(RuntimeError):
+        embed_match_softmax(torch.zeros((4, 8)), torch.zeros((2, 8)))          # CPU tensors
+    with pytest.raises(ValueError):
+        embed_match_softmax(torch.zeros((4, 12), device="cuda"), torch.zeros((2, 12), device="cuda"))  # dim % 8
+    with pytest.raises(ValueError):
+        embed_match_softmax(torch.zeros((4, 8), device="cuda"), torch.zeros((513, 8), device="cuda"))
