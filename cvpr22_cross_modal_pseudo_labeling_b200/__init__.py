@@ -11,7 +11,7 @@ from . import _ext  # noqa: F401
 __version__ = "0.1.0"
 
 
-def build(force=False, verbose=False):
+def build_kernels(force=False, verbose=False):
     """Compile csrc/*.cu for sm_100a into libb200det.so (in-tree)."""
-    from . import build as _build
-    return _build.build(force=force, verbose=verbose)
+    import importlib
+    return importlib.import_module(__name__ + ".build").build(force=force, verbose=verbose)

@@ -1,0 +1,183 @@
+"""Generate the committed golden fixtures from the REFERENCE itself (run in the build
+container, where /root/reference exists; the GPU box only reads the .npz files).
+
+The reference's own CPU kernels (oracle/_ref, compiled in place from
+/root/reference/maskrcnn_benchmark/csrc/cpu) are plugged in as `maskrcnn_benchmark._C`, and
+the reference's own Python classes (Pooler, RPNPostProcessor, PostProcessor,
+FastRCNNPredictor) are imported from /root/reference and driven on seeded synthetic inputs.
+
+    python tests/golden/make_golden.py        # rewrites tests/golden/*.npz
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+import oracle  # noqa: E402
+from tests import synth  # noqa: E402
+
+REF = "/root/reference"
+
+
+def install_reference():
+    """apex.amp / maskrcnn_benchmark._C stubs so the reference's Python imports on CPU."""
+    np.float = float  # rpn/anchor_generator.py uses the removed alias
+    amp = types.ModuleType("apex.amp")
+    amp.float_function = lambda f: f
+    apex = types.ModuleType("apex")
+    apex.amp = amp
+    sys.modules["apex"], sys.modules["apex.amp"] = apex, amp
+    sys.path.insert(0, REF)
+    import maskrcnn_benchmark
+    c = types.ModuleType("maskrcnn_benchmark._C")
+
+    def nms(dets, scores, thr):
+        return torch.from_numpy(oracle.ref_nms(dets.numpy(), scores.numpy(), float(thr)))
+
+    def roi_align_forward(inp, rois, scale, ph, pw, sr):
+        return torch.from_numpy(oracle.ref_roi_align_forward(inp.contiguous().numpy(), rois.contiguous().numpy(),
+                                                             float(scale), int(ph), int(pw), int(sr)))
+    c.nms = nms
+    c.roi_align_forward = roi_align_forward
+    sys.modules["maskrcnn_benchmark._C"] = c
+    maskrcnn_benchmark._C = c
+
+
+def gen_roi_align(rng):
+    out = {}
+    cases = [(2, 16, 25, 42, 1 / 32, 7, 7, 2, 40), (1, 8, 50, 84, 1 / 16, 14, 14, 0, 30), (1, 8, 30, 30, 1 / 8, 3, 5, 3, 20)]
+    for i, (b, c, h, w, scale, ph, pw, sr, n) in enumerate(cases):
+        x = rng.standard_normal((b, c, h, w)).astype(np.float32)
+        rois = synth.make_rois(rng, n, b, int(w / scale), int(h / scale), smin=4, smax=float(max(w, h) / scale))
+        rois[0, 3] = rois[0, 1] - 3          # malformed
+        rois[1, 1:] += 9000                  # outside
+        out["ra%d_x" % i] = x
+        out["ra%d_rois" % i] = rois
+        out["ra%d_cfg" % i] = np.array([scale, ph, pw, sr], np.float64)
+        out["ra%d_out" % i] = oracle.ref_roi_align_forward(x, rois, scale, ph, pw, sr)
+    return out
+
+
+def gen_nms(rng):
+    out = {}
+    for i, (n, thr) in enumerate([(1, 0.5), (65, 0.5), (700, 0.7), (3000, 0.7)]):
+        b, s = synth.make_nms_boxes(rng, n)
+        out["nms%d_boxes" % i], out["nms%d_scores" % i] = b, s
+        out["nms%d_thr" % i] = np.array([thr])
+        out["nms%d_keep" % i] = oracle.ref_nms(b, s, thr)
+    return out
+
+
+def gen_pooler(rng):
+    from maskrcnn_benchmark.modeling.poolers import Pooler
+    from maskrcnn_benchmark.structures.bounding_box import BoxList
+    b, c, n = 2, 8, 60
+    shapes = synth.fpn_shapes(256, 416)
+    feats = [rng.standard_normal((b, c, h, w)).astype(np.float32) for (h, w) in shapes]
+    rois = synth.make_rois(rng, n, b, 416, 256, smin=8, smax=300)
+    boxes = [BoxList(torch.from_numpy(rois[i * n:(i + 1) * n, 1:].copy()), (416, 256)) for i in range(b)]
+    out = {}
+    for res in (7, 14):
+        y = Pooler((res, res), synth.FPN_SCALES, 2)([torch.from_numpy(f) for f in feats], boxes)
+        out["pool_out%d" % res] = y.numpy()
+    for l, f in enumerate(feats):
+        out["pool_f%d" % l] = f
+    out["pool_rois"] = rois
+    return out
+
+
+def gen_rpn(rng):
+    from maskrcnn_benchmark.modeling.box_coder import BoxCoder
+    from maskrcnn_benchmark.modeling.rpn.anchor_generator import AnchorGenerator
+    from maskrcnn_benchmark.modeling.rpn.inference import RPNPostProcessor
+    from maskrcnn_benchmark.structures.image_list import ImageList
+    n_img, img_h, img_w = 2, 256, 416
+    strides = (4, 8, 16)
+    sizes = (32, 64, 128)
+    ag = AnchorGenerator(sizes=sizes, aspect_ratios=(0.5, 1.0, 2.0), anchor_strides=strides, straddle_thresh=0)
+    feats = [torch.zeros(n_img, 1, img_h // s, img_w // s) for s in strides]
+    images = ImageList(torch.zeros(n_img, 3, img_h, img_w), [(img_h, img_w)] * n_img)
+    anchors = ag(images, feats)
+    # objectness with unique values per (image, level) so top-k has no ties
+    obj, reg = [], []
+    for f in feats:
+        h, w = f.shape[-2:]
+        a = 3
+        vals = rng.permutation(n_img * a * h * w).astype(np.float32) / (n_img * a * h * w) * 8 - 4
+        obj.append(torch.from_numpy(vals.reshape(n_img, a, h, w)))
+        reg.append(torch.from_numpy((rng.standard_normal((n_img, 4 * a, h, w)) * 0.3).astype(np.float32)))
+    out = {}
+    for tag, kw in (("test", dict(pre_nms_top_n=600, post_nms_top_n=100, fpn_post_nms_top_n=150)),
+                    ("single", dict(pre_nms_top_n=500, post_nms_top_n=80))):
+        pp = RPNPostProcessor(nms_thresh=0.7, min_size=0, box_coder=BoxCoder((1., 1., 1., 1.)), **kw)
+        pp.eval()
+        if tag == "single":
+            res = pp([[a[1]] for a in anchors], obj[1:2], reg[1:2])
+        else:
+            res = pp(anchors, obj, reg)
+        for i, bl in enumerate(res):
+            out["rpn_%s_boxes%d" % (tag, i)] = bl.bbox.numpy()
+            out["rpn_%s_obj%d" % (tag, i)] = bl.get_field("objectness").numpy()
+    for l in range(len(strides)):
+        out["rpn_obj%d" % l] = obj[l].numpy()
+        out["rpn_reg%d" % l] = reg[l].numpy()
+        for i in range(n_img):
+            out["rpn_anchors_%d_%d" % (i, l)] = anchors[i][l].bbox.numpy()
+    out["rpn_imsize"] = np.array([img_w, img_h])
+    return out
+
+
+def gen_box_head(rng):
+    from maskrcnn_benchmark.modeling.box_coder import BoxCoder
+    from maskrcnn_benchmark.modeling.roi_heads.box_head.inference import PostProcessor
+    from maskrcnn_benchmark.structures.bounding_box import BoxList
+    n_img, r, c, d = 2, 300, 20, 64
+    g = torch.Generator().manual_seed(77)
+    A = (torch.randn((n_img * r, d), generator=g) * 4).to(torch.bfloat16).float()
+    E = torch.nn.functional.normalize(torch.randn((c, d), generator=g), dim=-1)
+    E[0] = 0
+    E = E.to(torch.bfloat16).float()
+    logits = torch.einsum("pe,ce->pc", A, E)              # roi_box_predictors.py:67
+    reg = torch.randn((n_img * r, 8), generator=g) * 0.5
+    rois = synth.make_rois(rng, r, n_img, 640, 480, smin=16, smax=300)
+    boxes = [BoxList(torch.from_numpy(rois[i * r:(i + 1) * r, 1:].copy()), (640, 480)) for i in range(n_img)]
+    out = dict(bh_A=A.numpy(), bh_E=E.numpy(), bh_logits=logits.numpy(), bh_reg=reg.numpy(), bh_rois=rois)
+    pp = PostProcessor(0.05, 0.5, 100, BoxCoder((10., 10., 5., 5.)), cls_agnostic_bbox_reg=True)
+    res = pp((logits, reg), boxes)
+    for i, bl in enumerate(res):
+        out["bh_boxes%d" % i] = bl.bbox.numpy()
+        out["bh_scores%d" % i] = bl.get_field("scores").numpy()
+        out["bh_labels%d" % i] = bl.get_field("labels").numpy()
+    boxes = [BoxList(torch.from_numpy(rois[i * r:(i + 1) * r, 1:].copy()), (640, 480)) for i in range(n_img)]
+    tp = PostProcessor(0.05, 0.5, 100, BoxCoder((10., 10., 5., 5.)), cls_agnostic_bbox_reg=True, is_teacher=True)
+    res = tp((logits, reg), boxes)
+    out["bh_teacher_boxes0"] = res[0].bbox.numpy()
+    out["bh_teacher_scores0"] = res[0].get_field("scores").numpy()
+    # caption alignment, st_generalized_rcnn.py:245-255 (plain torch ops there)
+    W = torch.nn.functional.normalize(torch.randn((5, d), generator=g), dim=-1).to(torch.bfloat16).float()
+    rs = torch.einsum("pd,wd->pw", A[:r], W)
+    mx, idx = torch.max(rs, dim=0)
+    out.update(cap_W=W.numpy(), cap_idx=idx.numpy(), cap_max=mx.numpy(), cap_sig=torch.sigmoid(mx).numpy())
+    return out
+
+
+def main():
+    install_reference()
+    rng = np.random.default_rng(20221017)
+    np.savez_compressed(os.path.join(HERE, "roi_align.npz"), **gen_roi_align(rng))
+    np.savez_compressed(os.path.join(HERE, "nms.npz"), **gen_nms(rng))
+    np.savez_compressed(os.path.join(HERE, "pooler.npz"), **gen_pooler(rng))
+    np.savez_compressed(os.path.join(HERE, "rpn.npz"), **gen_rpn(rng))
+    np.savez_compressed(os.path.join(HERE, "box_head.npz"), **gen_box_head(rng))
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KB")
+
+
+if __name__ == "__main__":
+    main()

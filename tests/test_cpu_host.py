@@ -1,0 +1,143 @@
+"""CPU suite: the C-ABI library exports what include/b200det.h declares, the host-side
+mirrors behave like the reference containers, the product path refuses CPU tensors and never
+touches the oracle, and the N>1 sharding logic works under gloo (world_size 2)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "cvpr22_cross_modal_pseudo_labeling_b200")
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "b200det.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from cvpr22_cross_modal_pseudo_labeling_b200 import _ext
+    assert os.path.exists(_ext.LIB_PATH), "build the library first (__graft_entry__.build())"
+    lib = ctypes.CDLL(_ext.LIB_PATH)
+    names = _header_symbols()
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(lib, n), n
+    assert set(names) == set(_ext.SIGNATURES), "ctypes signatures out of sync with the header"
+    assert _ext.lib().b200_version() == 100
+
+
+def test_library_is_sm100a_with_tcgen05_and_tma():
+    from cvpr22_cross_modal_pseudo_labeling_b200 import _ext
+    if not os.path.exists("/usr/local/cuda/bin/cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-sass", _ext.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):       # tcgen05.mma, TMA tensor load, tcgen05.ld
+        assert mnemonic in out, mnemonic
+
+
+def test_product_never_imports_the_oracle():
+    for dp, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                txt = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+                assert "liboracle" not in txt and "libref_cpu" not in txt, f
+
+
+def test_cpu_tensors_are_rejected_everywhere():
+    from cvpr22_cross_modal_pseudo_labeling_b200.layers import ROIAlign, ROIPool, embed_match_softmax, nms
+    from cvpr22_cross_modal_pseudo_labeling_b200.modeling import Pooler
+    from cvpr22_cross_modal_pseudo_labeling_b200.structures import BoxList
+    x = torch.zeros(1, 64, 8, 8)
+    rois = torch.tensor([[0, 1.0, 1.0, 5.0, 5.0]])
+    with pytest.raises(RuntimeError):
+        ROIAlign((7, 7), 0.25, 2)(x, rois)
+    with pytest.raises(RuntimeError):
+        ROIPool((7, 7), 0.25)(x, rois)
+    with pytest.raises(RuntimeError):
+        nms(rois[:, 1:], torch.ones(1), 0.5)
+    with pytest.raises(RuntimeError):
+        embed_match_softmax(torch.zeros(4, 8), torch.zeros(2, 8))
+    with pytest.raises(RuntimeError):
+        Pooler((7, 7), (0.25, 0.125), 2)([x, x[:, :, ::2, ::2]], [BoxList(rois[:, 1:], (32, 32))])
+
+
+def test_boxlist_semantics():
+    from cvpr22_cross_modal_pseudo_labeling_b200.structures import BoxList, boxlist_iou, cat_boxlist, remove_small_boxes
+    b = BoxList(torch.tensor([[0., 0., 9., 9.], [5., 0., 14., 9.], [-5., -5., 700., 3.]]), (640, 480))
+    b.add_field("scores", torch.tensor([0.9, 0.8, 0.7]))
+    assert b.area().tolist()[:2] == [100.0, 100.0]                       # legacy +1 (bounding_box.py:226-230)
+    xywh = b.convert("xywh")
+    assert xywh.bbox[0].tolist() == [0, 0, 10, 10] and xywh.convert("xyxy").bbox[1].tolist() == [5, 0, 14, 9]
+    iou = boxlist_iou(b, b)
+    assert abs(float(iou[0, 1]) - 1 / 3) < 1e-6
+    c = BoxList(b.bbox.clone(), b.size).clip_to_image(remove_empty=False)
+    assert c.bbox[2].tolist() == [0, 0, 639, 3]
+    assert len(remove_small_boxes(c, 5)) == 2
+    both = cat_boxlist([b, b[torch.tensor([1])]])
+    assert len(both) == 4 and both.get_field("scores").tolist()[-1] == pytest.approx(0.8)
+    assert len(b[torch.tensor([True, False, True])]) == 2
+    r = b.resize((320, 240))
+    assert r.size == (320, 240) and r.bbox[0].tolist() == [0, 0, 4.5, 4.5]
+
+
+def test_box_coder_matches_oracle_decode():
+    import oracle
+    from cvpr22_cross_modal_pseudo_labeling_b200.modeling import BoxCoder
+    rng = np.random.default_rng(1)
+    anchors = np.abs(rng.standard_normal((500, 4)).astype(np.float32)) * 50
+    anchors[:, 2:] += anchors[:, :2] + 4
+    codes = (rng.standard_normal((500, 4)) * 2).astype(np.float32)
+    codes[:5, 2:] = 50.0                                                     # hits the log(1000/16) clamp
+    got = BoxCoder((10., 10., 5., 5.)).decode(torch.from_numpy(codes), torch.from_numpy(anchors)).numpy()
+    want = oracle.box_decode(codes, anchors, (10., 10., 5., 5.))
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-3)
+    enc = BoxCoder((10., 10., 5., 5.)).encode(torch.from_numpy(want), torch.from_numpy(anchors))
+    np.testing.assert_allclose(enc.numpy()[5:], codes[5:], rtol=1e-3, atol=1e-3)
+
+
+def test_shard_range_partitions_everything():
+    from cvpr22_cross_modal_pseudo_labeling_b200.parallel import shard_range
+    for n in (0, 1, 7, 64, 65):
+        for ws in (1, 2, 3, 8):
+            spans = [shard_range(n, r, ws) for r in range(ws)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["REPO_ROOT"])
+from cvpr22_cross_modal_pseudo_labeling_b200.parallel import all_gather_records, shard_range
+dist.init_process_group("gloo", init_method="env://")
+rank, ws = dist.get_rank(), dist.get_world_size()
+n_img = 5
+lo, hi = shard_range(n_img)
+rec = torch.zeros((hi - lo, 4, 8)); cnt = torch.zeros((hi - lo,), dtype=torch.int32)
+for i in range(lo, hi):
+    rec[i - lo, :, 0] = i; rec[i - lo, :, 6] = 0.1 * i; cnt[i - lo] = i % 4
+allr, allc = all_gather_records(rec, cnt)
+assert allr.shape == (n_img, 4, 8) and allc.tolist() == [i % 4 for i in range(n_img)], (allr.shape, allc)
+assert allr[:, 0, 0].tolist() == list(range(n_img))
+dist.barrier(); dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_all_gather_records_two_ranks_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, REPO_ROOT=ROOT, MASTER_ADDR="127.0.0.1", MASTER_PORT="29613", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
