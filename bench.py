@@ -1,0 +1,496 @@
+#!/usr/bin/env python
+"""bench.py -- RoI pseudo-labeling hot path on N B200s (one process per GPU).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --steps 2 --warmup 1     # the reference's CPU path, host cores
+
+Workload (BASELINE.json configs[1]): 16 synthetic COCO-shaped images per GPU (800x1333 padded
+to 800x1344), 256-channel fp32 FPN features P2-P5 (channels_last), RPN candidates on 5 levels
+(6000/6000/6000/3150/819 per image), 1000 proposals per image.
+
+One step = one pass of the hot path over the batch:
+  1. batched RPN NMS (80 segments, IoU 0.7, keep <= 1000 per level)      b200_nms_batched
+  2. per-image top-1000 over levels (torch.topk glue, as rpn/inference.py:173-180)
+  3. fused 4-level RoIAlign 7x7 on 16000 RoIs                            b200_roi_align_forward
+  4. head stub: mean-pool + Linear(256->768) (cuBLAS, stands in for res5/fc6-7) -> bf16
+  5. class-embedding match, 66 classes, softmax + top-1 fused              b200_embed_match
+  6. caption alignment, 1-10 nouns per image (column max + sigmoid)        b200_embed_match + decode
+  7. fused RoIAlign 14x14 (mask pooler) on the aligned pseudo-label boxes  b200_roi_align_forward
+  8. pack fixed-size pseudo-label records; N > 1: NCCL all-gather of the records
+
+Prints ONE JSON line (see the field notes in DESIGN.md, "Measurement").
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from tests import synth  # noqa: E402
+
+METRIC = "RoIs/sec pooled+scored (images/sec pseudo-labeled = value/1000)"
+UNIT = "RoIs/s"
+B_IMG = 16
+R_IMG = 1000
+C_FEAT = 256
+N_CLASSES = 66
+EMB_DIM = 768
+RPN_LENS = [6000, 6000, 6000, 3150, 819]  # min(6000, 3*H*W) on P2..P6 (reference PRE_NMS_TOP_N_TEST)
+WORKLOAD = ("roi_hot_path microbench: %d img/GPU x %d proposals, 5-level RPN NMS (6000/level, thr 0.7, keep 1000), "
+            "4-level RoIAlign 7x7 sr2 on 256ch fp32, 66-class embedding match D=768, caption alignment, "
+            "14x14 mask pooler on aligned boxes" % (B_IMG, R_IMG))
+
+
+# --------------------------------------------------------------------------------------------
+# synthetic inputs (seeded)
+# --------------------------------------------------------------------------------------------
+def make_rpn_candidates(rng, n_img):
+    bs, ss = [], []
+    for _ in range(n_img):
+        for L in RPN_LENS:
+            b, s = synth.make_nms_boxes(rng, L)
+            o = np.argsort(-s, kind="stable")  # RPN top-k output arrives score-sorted
+            bs.append(b[o])
+            ss.append(s[o])
+    return np.concatenate(bs), np.concatenate(ss)
+
+
+def make_text(seed, n_img):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    E = torch.nn.functional.normalize(torch.randn((N_CLASSES, EMB_DIM), generator=g), dim=-1)
+    E[0] = 0
+    nw = torch.randint(1, 11, (n_img,), generator=g).tolist()
+    words = [torch.nn.functional.normalize(torch.randn((w, EMB_DIM), generator=g), dim=-1) for w in nw]
+    Wfc = torch.randn((EMB_DIM, C_FEAT), generator=g) * 0.3
+    return E, words, Wfc
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU code (oracle/_ref, compiled from /root/reference in the
+# build container) on the host cores, one image per worker process
+# --------------------------------------------------------------------------------------------
+def _ref_image(seed):
+    """The same hot path for ONE image through the reference CPU kernels.  Returns seconds."""
+    import oracle
+    rng = np.random.default_rng(seed)
+    feats = [rng.standard_normal((1, C_FEAT, h, w), dtype=np.float32) for (h, w) in synth.fpn_shapes()]
+    boxes, scores = make_rpn_candidates(rng, 1)
+    g = np.random.default_rng(seed + 1)
+    E = g.standard_normal((N_CLASSES, EMB_DIM)).astype(np.float32)
+    E /= np.linalg.norm(E, axis=1, keepdims=True)
+    E[0] = 0
+    W = g.standard_normal((5, EMB_DIM)).astype(np.float32)
+    Wfc = (g.standard_normal((EMB_DIM, C_FEAT)) * 0.3).astype(np.float32)
+    use_ref = oracle.ref_lib() is not None
+    nms = oracle.ref_nms if use_ref else oracle.nms
+    ra = oracle.ref_roi_align_forward if use_ref else oracle.roi_align_forward
+    t0 = time.perf_counter()
+    # RPN NMS per level (rpn/inference.py:111-122), then per-image top-1000 (:173-180)
+    kb, ks, o = [], [], 0
+    for L in RPN_LENS:
+        k = nms(boxes[o:o + L], scores[o:o + L], 0.7)[:1000]
+        kb.append(boxes[o:o + L][k])
+        ks.append(scores[o:o + L][k])
+        o += L
+    kb, ks = np.concatenate(kb), np.concatenate(ks)
+    top = np.argsort(-ks, kind="stable")[:R_IMG]
+    rois = np.concatenate([np.zeros((len(top), 1), np.float32), kb[top]], 1)
+    # Pooler.forward (poolers.py:91-121)
+    lv = oracle.level_map(rois, 2.0, 5.0)
+    pooled = np.zeros((len(rois), C_FEAT, 7, 7), np.float32)
+    for l, (f, s) in enumerate(zip(feats, synth.FPN_SCALES)):
+        idx = np.nonzero(lv == l)[0]
+        if len(idx):
+            pooled[idx] = ra(f, rois[idx], s, 7, 7, 2)
+    emb = pooled.mean(axis=(2, 3)) @ Wfc.T
+    probs = oracle.softmax_rows(emb @ E.T)                       # roi_box_predictors.py:67, inference.py:62
+    sc = emb @ W.T                                               # st_generalized_rcnn.py:245-255
+    idx = sc.argmax(0)
+    _ = 1 / (1 + np.exp(-sc[idx, np.arange(W.shape[0])]))
+    sel = rois[idx]
+    lv = oracle.level_map(sel, 2.0, 5.0)
+    for l, (f, s) in enumerate(zip(feats, synth.FPN_SCALES)):
+        j = np.nonzero(lv == l)[0]
+        if len(j):
+            ra(f, sel[j], s, 14, 14, 2)
+    dt = time.perf_counter() - t0
+    assert probs.shape == (R_IMG, N_CLASSES)
+    return dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import multiprocessing as mp
+    import oracle
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, 32))
+    kind = "reference" if oracle.ref_lib() is not None else "port"
+    ctx = mp.get_context("fork")
+    times = []
+    with ctx.Pool(workers) as pool:
+        for it in range(args.warmup + args.steps):
+            # workers run concurrently; a step lasts as long as its slowest image (input
+            # generation inside the worker is outside its timed region)
+            dts = pool.map(_ref_image, [1000 + 97 * it + w for w in range(workers)])
+            if it >= args.warmup:
+                times.append(max(dts))
+    ms = 1e3 * float(np.mean(times)) if times else float("nan")
+    value = workers * R_IMG / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": "%d images per step, one per worker process" % workers},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": kind,
+                         "sample": "%d images/step (1 per worker), csrc kernels single-threaded as shipped" % workers},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------------------------
+# clocks sampler (NVML, background thread)
+# --------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+def f_touched_bytes(rois, levels, shapes, scales, channels):
+    """Exact union, per level, of the feature pixels inside the tap rectangle of the RoIs assigned
+    to the level, in bytes (fp32, all images)."""
+    import torch
+    total = 0
+    for l, ((h, w), s) in enumerate(zip(shapes, scales)):
+        m = levels == l
+        if not bool(m.any()):
+            continue
+        r = rois[m]
+        b = r[:, 0].long()
+        x0 = (r[:, 1] * s).floor().clamp(0, w - 1).long()
+        y0 = (r[:, 2] * s).floor().clamp(0, h - 1).long()
+        x1 = ((r[:, 3] * s).floor() + 1).clamp(0, w - 1).long()
+        y1 = ((r[:, 4] * s).floor() + 1).clamp(0, h - 1).long()
+        x1, y1 = torch.maximum(x1, x0), torch.maximum(y1, y0)
+        nb = int(b.max().item()) + 1
+        d = torch.zeros((nb, h + 1, w + 1), dtype=torch.int32, device=rois.device)
+        one = torch.ones_like(b, dtype=torch.int32)
+        d.index_put_((b, y0, x0), one, accumulate=True)
+        d.index_put_((b, y1 + 1, x0), -one, accumulate=True)
+        d.index_put_((b, y0, x1 + 1), -one, accumulate=True)
+        d.index_put_((b, y1 + 1, x1 + 1), one, accumulate=True)
+        cov = d.cumsum(1).cumsum(2)[:, :h, :w] > 0
+        total += int(cov.sum().item()) * channels * 4
+    return total
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from cvpr22_cross_modal_pseudo_labeling_b200 import _ext
+    from cvpr22_cross_modal_pseudo_labeling_b200.layers import caption_align, embed_match_softmax, nms_batched
+    from cvpr22_cross_modal_pseudo_labeling_b200.layers.roi_align import _forward as roi_align_forward
+    from cvpr22_cross_modal_pseudo_labeling_b200.parallel import all_gather_records
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (the B200 path has no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _ext.lib()
+    _ext.debug_set(False, not args.fma, 0)
+
+    seed = 1236 + 1000 * rank
+    rng = np.random.default_rng(seed)
+    shapes = synth.fpn_shapes()
+    scales = synth.FPN_SCALES
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    # ---- host (pinned) copies of every input the step consumes ----
+    feats_h = [torch.empty((B_IMG, h, w, C_FEAT), dtype=torch.float32).pin_memory() for (h, w) in shapes]
+    feats = []
+    for fh, (h, w) in zip(feats_h, shapes):
+        f = torch.randn((B_IMG, h, w, C_FEAT), device=dev, generator=gen)
+        fh.copy_(f)
+        feats.append(f.permute(0, 3, 1, 2))  # logical [B,C,H,W], channels_last memory
+    cb, cs = make_rpn_candidates(rng, B_IMG)
+    K = sum(RPN_LENS)
+    cand_boxes_h = torch.from_numpy(cb).pin_memory()
+    cand_scores_h = torch.from_numpy(cs).pin_memory()
+    seg_off = torch.from_numpy(np.concatenate([[0], np.cumsum(RPN_LENS * B_IMG)]).astype(np.int32)).to(dev)
+    E, words, Wfc = make_text(seed, B_IMG)
+    E_h = E.to(torch.bfloat16).pin_memory()
+    words_h = [w.to(torch.bfloat16).pin_memory() for w in words]
+    n_words = [int(w.shape[0]) for w in words]
+    Wfc_d = Wfc.to(dev)
+    batch_col = torch.arange(B_IMG, device=dev, dtype=torch.float32).repeat_interleave(R_IMG)[:, None]
+    img_of_word = torch.repeat_interleave(torch.arange(B_IMG, device=dev), torch.tensor(n_words, device=dev))
+    w_max = 10
+    h2d_bytes = sum(f.numel() * 4 for f in feats_h) + cand_boxes_h.numel() * 4 + cand_scores_h.numel() * 4 + \
+        E_h.numel() * 2 + sum(w.numel() * 2 for w in words_h)
+
+    state = {}
+    ev = {k: (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for k in ("nms", "pool7", "match", "pool14")}
+    acc = {k: [] for k in ev}
+
+    def step(cand_boxes, cand_scores, feats_d, E_d, words_d, timed=False):
+        def mark(k, i):
+            if timed:
+                ev[k][i].record()
+        # 1. batched RPN NMS
+        mark("nms", 0)
+        keep_idx, keep_cnt = nms_batched(cand_boxes, cand_scores, seg_off, 0.7, 1000, max(RPN_LENS))
+        mark("nms", 1)
+        # 2. kept flags -> per-image top-1000 (no host sync)
+        n = cand_boxes.shape[0]
+        seg_len = (seg_off[1:] - seg_off[:-1]).long()
+        seg_id = torch.repeat_interleave(torch.arange(seg_len.numel(), device=dev), seg_len, output_size=n)
+        start = seg_off[:-1].long()[seg_id]
+        pos = torch.arange(n, device=dev)
+        valid = (pos - start) < keep_cnt.long()[seg_id]
+        tgt = torch.where(valid, start + keep_idx.clamp(min=0), torch.full_like(pos, n))
+        kept = torch.zeros(n + 1, dtype=torch.bool, device=dev)
+        kept[tgt] = True
+        masked = torch.where(kept[:-1], cand_scores, torch.full_like(cand_scores, -1.0)).view(B_IMG, K)
+        _, top_i = masked.topk(R_IMG, dim=1, sorted=True)
+        props = cand_boxes.view(B_IMG, K, 4).gather(1, top_i[:, :, None].expand(-1, -1, 4)).reshape(-1, 4)
+        rois = torch.cat([batch_col, props], dim=1)
+        # 3. box pooler
+        mark("pool7", 0)
+        pooled, levels = roi_align_forward(feats_d, scales, rois, (7, 7), 2, want_levels=True)
+        mark("pool7", 1)
+        # 4. head stub (library GEMM): mean-pool + fc -> bf16 embeddings
+        emb = torch.nn.functional.linear(pooled.mean(dim=(2, 3)), Wfc_d).to(torch.bfloat16)
+        # 5-6. scoring + caption alignment
+        mark("match", 0)
+        cls = embed_match_softmax(emb, E_d, 0.05, want_probs=True)
+        aligned = caption_align(emb, [R_IMG] * B_IMG, words_d)
+        mark("match", 1)
+        idx = torch.cat([a[0] for a in aligned])
+        sig = torch.cat([a[2] for a in aligned])
+        sel = rois[img_of_word * R_IMG + idx]
+        # 7. mask pooler on the aligned boxes
+        mark("pool14", 0)
+        mask_feat, _ = roi_align_forward(feats_d, scales, sel, (14, 14), 2)
+        mark("pool14", 1)
+        # 8. records (img, word slot, box, score, region) + all-gather
+        rec = torch.zeros((B_IMG, w_max, 8), dtype=torch.float32, device=dev)
+        slot = torch.cat([torch.arange(w, device=dev) for w in n_words])
+        rec[img_of_word, slot] = torch.cat([img_of_word[:, None].float() + B_IMG * rank, slot[:, None].float(),
+                                            sel[:, 1:], sig[:, None], idx[:, None].float()], dim=1)
+        cnt = torch.tensor(n_words, dtype=torch.int32, device=dev)
+        if world > 1:
+            rec, cnt = all_gather_records(rec, cnt)
+        state.update(rois=rois, levels=levels, rec=rec, cnt=cnt, probs=cls["probs"], mask_feat=mask_feat, sel=sel)
+        return rec, cnt
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident inputs ----
+    cand_boxes = cand_boxes_h.to(dev)
+    cand_scores = cand_scores_h.to(dev)
+    E_d = E_h.to(dev)
+    words_d = [w.to(dev) for w in words_h]
+
+    for _ in range(args.warmup):
+        step(cand_boxes, cand_scores, feats, E_d, words_d)
+    sync_all()
+    sampler = ClockSampler(local)
+    sampler.start()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        step(cand_boxes, cand_scores, feats, E_d, words_d)
+    t1.record()
+    sync_all()
+    clocks = sampler.stop()
+    ms_total = t0.elapsed_time(t1)
+
+    # per-kernel durations (separate pass so the events do not perturb the headline loop)
+    for _ in range(max(3, min(args.steps, 10))):
+        step(cand_boxes, cand_scores, feats, E_d, words_d, timed=True)
+        torch.cuda.synchronize()
+        for k in ev:
+            acc[k].append(ev[k][0].elapsed_time(ev[k][1]))
+    kms = {k: float(np.median(v)) for k, v in acc.items()}
+
+    # ---- end to end: host buffers in, host records out, copies inside the timed region ----
+    feats_e = [torch.empty(f.shape, dtype=torch.float32, device=dev) for f in feats_h]
+    cb_e, cs_e = torch.empty_like(cand_boxes), torch.empty_like(cand_scores)
+    E_e = torch.empty_like(E_d)
+    words_e = [torch.empty_like(w) for w in words_d]
+    rec_h = torch.empty((B_IMG * world, w_max, 8), dtype=torch.float32).pin_memory()
+    cnt_h = torch.empty((B_IMG * world,), dtype=torch.int32).pin_memory()
+
+    def step_e2e():
+        for d, s in zip(feats_e, feats_h):
+            d.copy_(s, non_blocking=True)
+        cb_e.copy_(cand_boxes_h, non_blocking=True)
+        cs_e.copy_(cand_scores_h, non_blocking=True)
+        E_e.copy_(E_h, non_blocking=True)
+        for d, s in zip(words_e, words_h):
+            d.copy_(s, non_blocking=True)
+        rec, cnt = step(cb_e, cs_e, [f.permute(0, 3, 1, 2) for f in feats_e], E_e, words_e)
+        rec_h.copy_(rec, non_blocking=True)
+        cnt_h.copy_(cnt, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller holds the records on the host
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        step_e2e()
+    sync_all()
+    t2, t3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t2.record()
+    for _ in range(e2e_steps):
+        step_e2e()
+    t3.record()
+    sync_all()
+    ms_e2e_total = t2.elapsed_time(t3)
+
+    # ---- max over ranks ----
+    tms = torch.tensor([ms_total, ms_e2e_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_step = float(tms[0]) / args.steps
+    ms_e2e = float(tms[1]) / e2e_steps
+    rois_per_step = world * B_IMG * R_IMG
+
+    line = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        ft = f_touched_bytes(state["rois"], state["levels"], shapes, scales, C_FEAT)
+        out_bytes = B_IMG * R_IMG * C_FEAT * 49 * 4
+        algo = ft + out_bytes + B_IMG * R_IMG * 20
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "roi_align_fwd_ncu.json"))).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        achieved = algo / (kms["pool7"] * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": rois_per_step / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "images_per_gpu": B_IMG, "rois_per_image": R_IMG,
+                       "feature_layout": "channels_last (NHWC memory, logical [B,C,H,W])",
+                       "roi_align_mode": "fma (<=1e-5 rel)" if args.fma else "exact (bit-identical to ROIAlign_cpu)",
+                       "l2": "inputs (1.46 GB features/GPU) exceed the 126 MB L2; no flush needed",
+                       "images_per_sec": world * B_IMG / (ms_step * 1e-3)},
+            "clocks": clocks,
+            "e2e": {"value": rois_per_step / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(rec_h.numel() * 4 + cnt_h.numel() * 4) // world},
+            "gpu_launches": args.steps * (4 + 2),  # nms, pool7, softmax match, colmax match + decode, pool14
+            "kernel_ms": kms,
+            "roofline": {"kernel": "roi_align_fwd_march (box pooler 7x7)", "bound": "hbm", "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                         "algorithmic_bytes": int(algo), "f_touched_bytes": int(ft), "traffic": traffic},
+        }
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2",
+                                      "--warmup", "1"], capture_output=True, text=True, timeout=600)
+                ref = json.loads(out.stdout.strip().splitlines()[-1])
+                line["cpu_baseline"] = ref["cpu_baseline"]
+            except Exception as e:
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
+                                        "sample": "failed: %s" % e}
+        else:
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
+                                    "sample": "only measured at N=1 (run --impl reference)"}
+        print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--fma", action="store_true", help="RoIAlign FMA mode (<=1e-5 rel) instead of bit-exact")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
