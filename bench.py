@@ -322,7 +322,7 @@ def run_gpu(args):
         pooled, levels = roi_align_forward(feats_d, scales, rois, (7, 7), 2, want_levels=True)
         mark("pool7", 1)
         # 4. head stub (library GEMM): mean-pool + fc -> bf16 embeddings
-        emb = torch.nn.functional.linear(pooled.mean(dim=(2, 3)), Wfc_d).to(torch.bfloat16)
+        emb = torch.nn.functional.linear(torch.nn.functional.adaptive_avg_pool2d(pooled, 1).flatten(1), Wfc_d).to(torch.bfloat16)
         # 5-6. scoring + caption alignment
         mark("match", 0)
         cls = embed_match_softmax(emb, E_d, 0.05, want_probs=True)

@@ -259,13 +259,15 @@ nms_sweep_kernel(const u64* __restrict__ mask, const int32_t* __restrict__ order
 // Work is sum_i kept_i * alive_later_i pair tests instead of N^2/2, and stops as soon as
 // max_keep boxes are kept when the segment arrived sorted (RPN top-k output does).
 // ---------------------------------------------------------------------------------------
-constexpr int kFusedMaxSeg = 13952;  // 16 B * n of dynamic shared memory next to ~8 KB static
+constexpr int kFusedMaxSeg = 12288;  // 16 B * n of dynamic shared memory + kept list next to ~8 KB static
+constexpr int kChunkBoxes = 1024;    // lazy-update granularity of the early-stopping sweep
 
 template <int kThreads>
 __global__ void __launch_bounds__(kThreads, 1)
 nms_fused_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores,
                  const int32_t* __restrict__ seg_off, int max_seg_len, float thresh, long long max_keep,
-                 int32_t* __restrict__ order, long long* __restrict__ keep_idx, int32_t* __restrict__ keep_cnt) {
+                 int kl_offset_boxes, int kl_capacity, int32_t* __restrict__ order,
+                 long long* __restrict__ keep_idx, int32_t* __restrict__ keep_cnt) {
   extern __shared__ __align__(16) unsigned char fused_smem[];
   float4* sb = reinterpret_cast<float4*>(fused_smem);  // boxes in visiting order
   u64* keys = reinterpret_cast<u64*>(fused_smem);      // aliases sb during the sort
@@ -333,79 +335,113 @@ nms_fused_kernel(const float4* __restrict__ boxes, const float* __restrict__ sco
 
   constexpr int G = kThreads / kTile;  // threads cooperating on one diagonal row
   constexpr int CPT = kTile / G;       // columns per thread
-  for (int i = 0; i < nb; ++i) {
-    const int base = i * kTile;
-    const int nrows = min(kTile, n - base);
-    const u64 gone0 = ((u64)remv[2 * i + 1] << 32) | remv[2 * i];
-    const u64 live_mask = nrows == 64 ? ~0ull : ((1ull << nrows) - 1);
-    if ((gone0 & live_mask) == live_mask) continue;  // whole tile already removed (uniform)
-
-    // (a) diagonal words: thread (row r, column group cg) tests CPT columns > r
-    {
-      const int r = tid / G, cg = tid % G;
-      u64 bits = 0;
-      if (r < nrows && !((gone0 >> r) & 1ull)) {
-        const float4 a = sb[base + r];
-        const float area_a = legacy_area(a);
-#pragma unroll 4
-        for (int k = 0; k < CPT; ++k) {
-          const int c = cg * CPT + k;
-          if (c > r && c < nrows) {
-            const float4 b = sb[base + c];
-            if (suppresses(a, area_a, b, legacy_area(b), thresh)) bits |= 1ull << c;
-          }
-        }
-      }
-#pragma unroll
-      for (int d = G / 2; d > 0; d >>= 1) bits |= __shfl_xor_sync(0xffffffffu, bits, d);
-      if (cg == 0) diag[r] = bits;
-    }
-    __syncthreads();
-    // (b) in-tile chain
-    if (tid == 0) {
-      u64 gone = gone0, kept = 0;
-#pragma unroll 8
-      for (int r = 0; r < nrows; ++r) {
-        const u64 d = diag[r];
-        if (!((gone >> r) & 1ull)) {
-          kept |= 1ull << r;
-          gone |= d;
-        }
-      }
-      s_kept = kept;
-      s_nkept += __popcll(kept);
-    }
-    __syncthreads();
-    const u64 kept = s_kept;
-    const int m = __popcll(kept);
-    if (tid < kTile && ((kept >> tid) & 1ull)) {
-      const int pos = __popcll(kept & ((1ull << tid) - 1));
-      const float4 b = sb[base + tid];
-      kb[pos] = b;
-      ka[pos] = legacy_area(b);
-      const int o = unsorted ? order[off + base + tid] : base + tid;
-      atomicOr(&keepbits[o >> 6], 1ull << (o & 63));
-    }
-    if (can_stop && (long long)s_nkept >= max_keep) break;  // uniform: shared value
-    __syncthreads();
-    // (c) later boxes vs this tile's kept boxes
-    for (int j0 = base + kTile + (tid & ~31); j0 < n; j0 += kThreads) {
-      const int j = j0 + lane;
-      const uint32_t dead = remv[j0 >> 5];
-      bool sup = false;
-      if (j < n && !((dead >> lane) & 1u)) {
-        const float4 b = sb[j];
+  // When the sweep may stop early (sorted input + max_keep), later boxes are only brought up
+  // to date in chunks of kChunkBoxes: a chunk is first tested against the list of ALL boxes
+  // kept so far (kl), then swept tile by tile with step (c) confined to the chunk.  Boxes
+  // beyond the chunk in which max_keep is reached are never touched.
+  float4* kl = reinterpret_cast<float4*>(fused_smem + sizeof(float4) * (size_t)kl_offset_boxes);
+  float* kla = reinterpret_cast<float*>(kl + kl_capacity);
+  const int chunk_boxes = can_stop ? kChunkBoxes : nb * kTile;
+  int nk = 0;  // boxes in kl (uniform)
+  bool done = false;
+  for (int c0 = 0; c0 < n && !done; c0 += chunk_boxes) {
+    const int c1 = min(n, c0 + chunk_boxes);
+    if (c0 > 0 && nk > 0) {
+      // chunk vs everything kept so far
+      for (int j0 = c0 + (tid & ~31); j0 < c1; j0 += kThreads) {
+        const int j = j0 + lane;
+        // warp-uniform trip count, predicated body: the lanes of a warp stay converged
+        // (a per-lane `break` made ptxas serialise the 32 lanes of this loop)
+        const uint32_t dead = remv[j0 >> 5];
+        bool alive = j < c1 && !((dead >> lane) & 1u);
+        const float4 b = sb[alive ? j : c0];
         const float area_b = legacy_area(b);
-        for (int r = 0; r < m; ++r)
-          if (suppresses(kb[r], ka[r], b, area_b, thresh)) {
-            sup = true;
-            break;
-          }
+        for (int r = 0; r < nk; ++r)
+          if (alive && suppresses(kl[r], kla[r], b, area_b, thresh)) alive = false;
+        const uint32_t v = __ballot_sync(0xffffffffu, j < c1 && !((dead >> lane) & 1u) && !alive);
+        if (lane == 0 && v) remv[j0 >> 5] = dead | v;
       }
-      const uint32_t v = __ballot_sync(0xffffffffu, sup);
-      if (lane == 0 && v) remv[j0 >> 5] = dead | v;
+      __syncthreads();
     }
-    __syncthreads();
+    for (int i = c0 / kTile; i * kTile < c1; ++i) {
+      const int base = i * kTile;
+      const int nrows = min(kTile, n - base);
+      const u64 gone0 = ((u64)remv[2 * i + 1] << 32) | remv[2 * i];
+      const u64 live_mask = nrows == 64 ? ~0ull : ((1ull << nrows) - 1);
+      if ((gone0 & live_mask) == live_mask) continue;  // whole tile already removed (uniform)
+
+      // (a) diagonal words: thread (row r, column group cg) tests CPT columns > r
+      {
+        const int r = tid / G, cg = tid % G;
+        u64 bits = 0;
+        if (r < nrows && !((gone0 >> r) & 1ull)) {
+          const float4 a = sb[base + r];
+          const float area_a = legacy_area(a);
+#pragma unroll 4
+          for (int k = 0; k < CPT; ++k) {
+            const int c = cg * CPT + k;
+            if (c > r && c < nrows) {
+              const float4 b = sb[base + c];
+              if (suppresses(a, area_a, b, legacy_area(b), thresh)) bits |= 1ull << c;
+            }
+          }
+        }
+#pragma unroll
+        for (int d = G / 2; d > 0; d >>= 1) bits |= __shfl_xor_sync(0xffffffffu, bits, d);
+        if (cg == 0) diag[r] = bits;
+      }
+      __syncthreads();
+      // (b) in-tile chain
+      if (tid == 0) {
+        u64 gone = gone0, kept = 0;
+#pragma unroll 8
+        for (int r = 0; r < nrows; ++r) {
+          const u64 d = diag[r];
+          if (!((gone >> r) & 1ull)) {
+            kept |= 1ull << r;
+            gone |= d;
+          }
+        }
+        s_kept = kept;
+        s_nkept += __popcll(kept);
+      }
+      __syncthreads();
+      const u64 kept = s_kept;
+      const int m = __popcll(kept);
+      if (tid < kTile && ((kept >> tid) & 1ull)) {
+        const int pos = __popcll(kept & ((1ull << tid) - 1));
+        const float4 b = sb[base + tid];
+        const float ab = legacy_area(b);
+        kb[pos] = b;
+        ka[pos] = ab;
+        if (can_stop && nk + pos < kl_capacity) {
+          kl[nk + pos] = b;
+          kla[nk + pos] = ab;
+        }
+        const int o = unsorted ? order[off + base + tid] : base + tid;
+        atomicOr(&keepbits[o >> 6], 1ull << (o & 63));
+      }
+      nk += m;
+      if (can_stop && (long long)s_nkept >= max_keep) {  // uniform: shared value
+        done = true;
+        break;
+      }
+      __syncthreads();
+      // (c) later boxes of this chunk vs this tile's kept boxes
+      for (int j0 = base + kTile + (tid & ~31); j0 < c1; j0 += kThreads) {
+        const int j = j0 + lane;
+        const uint32_t dead = remv[j0 >> 5];
+        const bool cand = j < c1 && !((dead >> lane) & 1u);
+        bool alive = cand;
+        const float4 b = sb[cand ? j : base];
+        const float area_b = legacy_area(b);
+        for (int r = 0; r < m; ++r)  // warp-uniform trip count, predicated body
+          if (alive && suppresses(kb[r], ka[r], b, area_b, thresh)) alive = false;
+        const uint32_t v = __ballot_sync(0xffffffffu, cand && !alive);
+        if (lane == 0 && v) remv[j0 >> 5] = dead | v;
+      }
+      __syncthreads();
+    }
   }
   __syncthreads();
 
@@ -439,6 +475,14 @@ nms_fused_kernel(const float4* __restrict__ boxes, const float* __restrict__ sco
 
 bool g_nms_force_bitmask = false;
 
+// the fused kernel needs the segment's boxes (+ the kept list) in one CTA's shared memory
+bool fused_applies(int64_t max_seg_len, int64_t max_keep) {
+  if (g_nms_force_bitmask || max_seg_len > kFusedMaxSeg) return false;
+  const size_t n_cap = (size_t)b200::ceil_div<int64_t>(max_seg_len, kTile) * kTile;
+  const size_t kl_cap = max_keep > 0 ? (size_t)(max_keep < max_seg_len ? max_keep : max_seg_len) + kTile : 0;
+  return sizeof(float4) * n_cap + (sizeof(float4) + sizeof(float)) * kl_cap + 8 * 1024 <= 227 * 1024;
+}
+
 struct Workspace {
   float4* sboxes;
   int32_t* order;
@@ -462,7 +506,7 @@ Workspace carve(void* base, int64_t n_total, int64_t n_segments, int64_t max_seg
   o = align_up(o + sizeof(int32_t) * (size_t)n_segments, 256);
   w.mask = reinterpret_cast<u64*>(p + o);
   // the bitmask exists only on the three-kernel path
-  if (max_seg_len > kFusedMaxSeg || g_nms_force_bitmask) o = align_up(o + sizeof(u64) * (size_t)n_total * MB, 256);
+  o = align_up(o + sizeof(u64) * (size_t)n_total * MB, 256);
   w.bytes = o;
   return w;
 }
@@ -500,24 +544,27 @@ extern "C" int b200_nms_batched(const float* boxes, const float* scores, const i
   }
   const int64_t kMaxGridX = 2147483647LL;
   B200_REQUIRE(n_segments <= kMaxGridX, "nms: too many segments");
-  if (max_seg_len <= kFusedMaxSeg && !g_nms_force_bitmask) {
-    const size_t smem = sizeof(float4) * (size_t)ceil_div<int64_t>(max_seg_len, kTile) * kTile;
+  const int n_cap = (int)ceil_div<int64_t>(max_seg_len, kTile) * kTile;
+  // kept-box list for the early-stopping sweep (only when max_keep is given)
+  const int kl_cap = max_keep > 0 ? (int)(max_keep < max_seg_len ? max_keep : max_seg_len) + kTile : 0;
+  const size_t smem = sizeof(float4) * (size_t)n_cap + (sizeof(float4) + sizeof(float)) * (size_t)kl_cap;
+  if (fused_applies(max_seg_len, max_keep)) {
     if (max_seg_len <= 1024) {
       auto kern = nms_fused_kernel<256>;
       int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                           "nms: cudaFuncSetAttribute");
       if (rc != B200_OK) return rc;
       kern<<<(unsigned)n_segments, 256, smem, st>>>(reinterpret_cast<const float4*>(boxes), scores, seg_offsets,
-                                                    (int)max_seg_len, thresh, (long long)max_keep, w.order,
-                                                    reinterpret_cast<long long*>(keep_idx), keep_cnt);
+                                                    (int)max_seg_len, thresh, (long long)max_keep, n_cap, kl_cap,
+                                                    w.order, reinterpret_cast<long long*>(keep_idx), keep_cnt);
     } else {
       auto kern = nms_fused_kernel<1024>;
       int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                           "nms: cudaFuncSetAttribute");
       if (rc != B200_OK) return rc;
       kern<<<(unsigned)n_segments, 1024, smem, st>>>(reinterpret_cast<const float4*>(boxes), scores, seg_offsets,
-                                                     (int)max_seg_len, thresh, (long long)max_keep, w.order,
-                                                     reinterpret_cast<long long*>(keep_idx), keep_cnt);
+                                                     (int)max_seg_len, thresh, (long long)max_keep, n_cap, kl_cap,
+                                                     w.order, reinterpret_cast<long long*>(keep_idx), keep_cnt);
     }
     B200_CHECK_LAUNCH("nms_fused_kernel");
     return B200_OK;

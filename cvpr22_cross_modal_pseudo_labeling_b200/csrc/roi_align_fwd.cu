@@ -257,8 +257,15 @@ roi_align_fwd_march(const LevelTable lt, int C, const float* __restrict__ rois, 
   constexpr int kQuads = kChunk / 4;
   const float* feat = lt.data[h.level] + (size_t)h.batch * H * W * C + c_begin;
   // ---- march: thread = (output row ph, channel quad q) ----------------------------------
-  for (int u = tid; u < PH * kQuads; u += kThreads) {
-    const int q = u % kQuads, ph = u / kQuads;
+  // Lane layout: a warp owns kQuadsPerWarp channel quads for ALL output rows (lane = ph *
+  // kQuadsPerWarp + quad), so the sectors a warp reads are read by no other warp of the CTA,
+  // and rows shared by neighbouring output rows are requested by the same warp back to back
+  // (L1 hits) -- each patch byte crosses L2 -> SM about once.
+  constexpr int kWarps = kThreads / 32;
+  constexpr int kQuadsPerWarp = kQuads / kWarps;  // 4 (PH <= 8) or 2 (PH <= 16)
+  {
+    const int q = warp * kQuadsPerWarp + (lane % kQuadsPerWarp), ph = lane / kQuadsPerWarp;
+    if (ph < PH) {
     const AxisEntry ya = ytab[2 * ph], yb = ytab[2 * ph + 1];
     const int rows[4] = {ya.lo + 4 * q, ya.hi + 4 * q, yb.lo + 4 * q, yb.hi + 4 * q};
     // Two register columns (4 tap rows x 4 channels each) ping-pong between the roles
@@ -295,6 +302,7 @@ roi_align_fwd_march(const LevelTable lt, int C, const float* __restrict__ rois, 
       o[NB + pw] = acc.y * 0.25f;
       o[2 * NB + pw] = acc.z * 0.25f;
       o[3 * NB + pw] = acc.w * 0.25f;
+    }
     }
   }
   __syncthreads();
@@ -336,9 +344,10 @@ int launch_forward(const LevelTable& lt, int layout, int C, const float* rois, i
                         C % kChunk == 0 && (NB * kChunk) % 4 == 0;
   B200_REQUIRE(n_rois * ((C + 15) / 16) < (int64_t)1 << 31, "roi_align: too many RoIs for one launch");
   if (march_ok) {
-    // g_variant (tuning hook): 0 = 5 CTAs/SM of 128 threads (3 of 256), 1 = 4 (2)
+    // g_variant (tuning hook): CTAs/SM = 5 (default) / 4 / 6 for 128 threads, 3 / 2 / 3 for 256
     if (PH * (kChunk / 4) <= 128) {
       if (g_variant == 1) return launch_march<kExact, 128, 4>(lt, C, rois, n_rois, PH, PW, out, out_levels, st);
+      if (g_variant == 2) return launch_march<kExact, 128, 6>(lt, C, rois, n_rois, PH, PW, out, out_levels, st);
       return launch_march<kExact, 128, 5>(lt, C, rois, n_rois, PH, PW, out, out_levels, st);
     }
     if (g_variant == 1) return launch_march<kExact, 256, 2>(lt, C, rois, n_rois, PH, PW, out, out_levels, st);

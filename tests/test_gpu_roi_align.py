@@ -62,7 +62,7 @@ def test_roi_align_forward_exact(case, nhwc):
     assert np.array_equal(got2.cpu().numpy(), want)
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("res", [7, 14])
 def test_roi_align_forward_occupancy_variants(variant, res):
     """Every register/occupancy variant of the marching kernel must stay bit-exact."""
