@@ -284,6 +284,7 @@ def run_gpu(args):
     words_h = [w.to(torch.bfloat16).pin_memory() for w in words]
     n_words = [int(w.shape[0]) for w in words]
     Wfc_d = Wfc.to(dev)
+    ones49 = torch.full((49,), 1.0 / 49.0, device=dev)
     batch_col = torch.arange(B_IMG, device=dev, dtype=torch.float32).repeat_interleave(R_IMG)[:, None]
     img_of_word = torch.repeat_interleave(torch.arange(B_IMG, device=dev), torch.tensor(n_words, device=dev))
     w_max = 10
@@ -322,7 +323,7 @@ def run_gpu(args):
         pooled, levels = roi_align_forward(feats_d, scales, rois, (7, 7), 2, want_levels=True)
         mark("pool7", 1)
         # 4. head stub (library GEMM): mean-pool + fc -> bf16 embeddings
-        emb = torch.nn.functional.linear(torch.nn.functional.adaptive_avg_pool2d(pooled, 1).flatten(1), Wfc_d).to(torch.bfloat16)
+        emb = torch.nn.functional.linear(torch.mv(pooled.view(-1, 49), ones49).view(-1, C_FEAT), Wfc_d).to(torch.bfloat16)
         # 5-6. scoring + caption alignment
         mark("match", 0)
         cls = embed_match_softmax(emb, E_d, 0.05, want_probs=True)

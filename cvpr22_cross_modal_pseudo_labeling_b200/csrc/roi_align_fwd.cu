@@ -257,14 +257,16 @@ roi_align_fwd_march(const LevelTable lt, int C, const float* __restrict__ rois, 
   constexpr int kQuads = kChunk / 4;
   const float* feat = lt.data[h.level] + (size_t)h.batch * H * W * C + c_begin;
   // ---- march: thread = (output row ph, channel quad q) ----------------------------------
-  // Lane layout: a warp owns kQuadsPerWarp channel quads for ALL output rows (lane = ph *
-  // kQuadsPerWarp + quad), so the sectors a warp reads are read by no other warp of the CTA,
-  // and rows shared by neighbouring output rows are requested by the same warp back to back
-  // (L1 hits) -- each patch byte crosses L2 -> SM about once.
-  constexpr int kWarps = kThreads / 32;
-  constexpr int kQuadsPerWarp = kQuads / kWarps;  // 4 (PH <= 8) or 2 (PH <= 16)
+  // Lane layout.  kThreads == 128 (PH <= 8): a warp owns 4 channel quads for ALL output rows
+  // (lane = ph * 4 + quad), so the sectors a warp reads are read by no other warp of the CTA
+  // and rows shared by neighbouring output rows are requested by the same warp back to back.
+  // kThreads == 256 (PH <= 16): 16 quads x 2 output rows per warp (full 256 B per pixel and
+  // request; measured faster than 2 quads x 16 rows for the 14x14 pooler).
+  constexpr int kLQ = kThreads == 128 ? 4 : 16;  // quads side by side in a warp
+  constexpr int kQGroups = kQuads / kLQ;         // warps needed to cover the 16 quads
   {
-    const int q = warp * kQuadsPerWarp + (lane % kQuadsPerWarp), ph = lane / kQuadsPerWarp;
+    const int q = (warp % kQGroups) * kLQ + (lane % kLQ);
+    const int ph = lane / kLQ + (32 / kLQ) * (warp / kQGroups);
     if (ph < PH) {
     const AxisEntry ya = ytab[2 * ph], yb = ytab[2 * ph + 1];
     const int rows[4] = {ya.lo + 4 * q, ya.hi + 4 * q, yb.lo + 4 * q, yb.hi + 4 * q};
@@ -344,13 +346,13 @@ int launch_forward(const LevelTable& lt, int layout, int C, const float* rois, i
                         C % kChunk == 0 && (NB * kChunk) % 4 == 0;
   B200_REQUIRE(n_rois * ((C + 15) / 16) < (int64_t)1 << 31, "roi_align: too many RoIs for one launch");
   if (march_ok) {
-    // g_variant (tuning hook): CTAs/SM = 5 (default) / 4 / 6 for 128 threads, 3 / 2 / 3 for 256
+    // g_variant (tuning hook): CTAs/SM = 6 (default) / 5 / 4 for 128 threads, 3 / 3 / 2 for 256
     if (PH * (kChunk / 4) <= 128) {
-      if (g_variant == 1) return launch_march<kExact, 128, 4>(lt, C, rois, n_rois, PH, PW, out, out_levels, st);
-      if (g_variant == 2) return launch_march<kExact, 128, 6>(lt, C, rois, n_rois, PH, PW, out, out_levels, st);
-      return launch_march<kExact, 128, 5>(lt, C, rois, n_rois, PH, PW, out, out_levels, st);
+      if (g_variant == 1) return launch_march<kExact, 128, 5>(lt, C, rois, n_rois, PH, PW, out, out_levels, st);
+      if (g_variant == 2) return launch_march<kExact, 128, 4>(lt, C, rois, n_rois, PH, PW, out, out_levels, st);
+      return launch_march<kExact, 128, 6>(lt, C, rois, n_rois, PH, PW, out, out_levels, st);
     }
-    if (g_variant == 1) return launch_march<kExact, 256, 2>(lt, C, rois, n_rois, PH, PW, out, out_levels, st);
+    if (g_variant == 2) return launch_march<kExact, 256, 2>(lt, C, rois, n_rois, PH, PW, out, out_levels, st);
     return launch_march<kExact, 256, 3>(lt, C, rois, n_rois, PH, PW, out, out_levels, st);
   }
   // generic: pick channels per CTA so that a CTA has >= ~2k units of work
