@@ -296,6 +296,23 @@ def run_gpu(args):
           for k in ("nms", "pool7", "match", "pool14")}
     acc = {k: [] for k in ev}
 
+    # static index helpers of the step (built once, so the step issues no host->device copies
+    # and can be replayed as a CUDA graph)
+    n_cand = cb.shape[0]
+    seg_len = (seg_off[1:] - seg_off[:-1]).long()
+    seg_id = torch.repeat_interleave(torch.arange(seg_len.numel(), device=dev), seg_len, output_size=n_cand)
+    slot_start = seg_off[:-1].long()[seg_id]
+    pos = torch.arange(n_cand, device=dev)
+    pos_rel = pos - slot_start
+    dummy = torch.full_like(pos, n_cand)
+    neg1 = torch.full((n_cand,), -1.0, device=dev)
+    word_slot = torch.cat([torch.arange(w, device=dev) for w in n_words])
+    cnt_words = torch.tensor(n_words, dtype=torch.int32, device=dev)
+    word_base = img_of_word * R_IMG
+    rec_img = (img_of_word.float() + B_IMG * rank)[:, None]
+    rec_slot = word_slot.float()[:, None]
+    rows_per_image = [R_IMG] * B_IMG
+
     def step(cand_boxes, cand_scores, feats_d, E_d, words_d, timed=False):
         def mark(k, i):
             if timed:
@@ -305,16 +322,11 @@ def run_gpu(args):
         keep_idx, keep_cnt = nms_batched(cand_boxes, cand_scores, seg_off, 0.7, 1000, max(RPN_LENS))
         mark("nms", 1)
         # 2. kept flags -> per-image top-1000 (no host sync)
-        n = cand_boxes.shape[0]
-        seg_len = (seg_off[1:] - seg_off[:-1]).long()
-        seg_id = torch.repeat_interleave(torch.arange(seg_len.numel(), device=dev), seg_len, output_size=n)
-        start = seg_off[:-1].long()[seg_id]
-        pos = torch.arange(n, device=dev)
-        valid = (pos - start) < keep_cnt.long()[seg_id]
-        tgt = torch.where(valid, start + keep_idx.clamp(min=0), torch.full_like(pos, n))
-        kept = torch.zeros(n + 1, dtype=torch.bool, device=dev)
-        kept[tgt] = True
-        masked = torch.where(kept[:-1], cand_scores, torch.full_like(cand_scores, -1.0)).view(B_IMG, K)
+        valid = pos_rel < keep_cnt.long()[seg_id]
+        tgt = torch.where(valid, slot_start + keep_idx.clamp(min=0), dummy)
+        kept = torch.zeros(n_cand + 1, dtype=torch.bool, device=dev)
+        kept.index_fill_(0, tgt, True)
+        masked = torch.where(kept[:-1], cand_scores, neg1).view(B_IMG, K)
         _, top_i = masked.topk(R_IMG, dim=1, sorted=True)
         props = cand_boxes.view(B_IMG, K, 4).gather(1, top_i[:, :, None].expand(-1, -1, 4)).reshape(-1, 4)
         rois = torch.cat([batch_col, props], dim=1)
@@ -322,30 +334,58 @@ def run_gpu(args):
         mark("pool7", 0)
         pooled, levels = roi_align_forward(feats_d, scales, rois, (7, 7), 2, want_levels=True)
         mark("pool7", 1)
-        # 4. head stub (library GEMM): mean-pool + fc -> bf16 embeddings
+        # 4. head stub (library GEMMs): mean-pool + fc -> bf16 embeddings
         emb = torch.nn.functional.linear(torch.mv(pooled.view(-1, 49), ones49).view(-1, C_FEAT), Wfc_d).to(torch.bfloat16)
         # 5-6. scoring + caption alignment
         mark("match", 0)
         cls = embed_match_softmax(emb, E_d, 0.05, want_probs=True)
-        aligned = caption_align(emb, [R_IMG] * B_IMG, words_d)
+        aligned = caption_align(emb, rows_per_image, words_d)
         mark("match", 1)
         idx = torch.cat([a[0] for a in aligned])
         sig = torch.cat([a[2] for a in aligned])
-        sel = rois[img_of_word * R_IMG + idx]
+        sel = rois[word_base + idx]
         # 7. mask pooler on the aligned boxes
         mark("pool14", 0)
         mask_feat, _ = roi_align_forward(feats_d, scales, sel, (14, 14), 2)
         mark("pool14", 1)
-        # 8. records (img, word slot, box, score, region) + all-gather
+        # 8. records (img, word slot, box, score, region)
         rec = torch.zeros((B_IMG, w_max, 8), dtype=torch.float32, device=dev)
-        slot = torch.cat([torch.arange(w, device=dev) for w in n_words])
-        rec[img_of_word, slot] = torch.cat([img_of_word[:, None].float() + B_IMG * rank, slot[:, None].float(),
-                                            sel[:, 1:], sig[:, None], idx[:, None].float()], dim=1)
-        cnt = torch.tensor(n_words, dtype=torch.int32, device=dev)
+        rec[img_of_word, word_slot] = torch.cat([rec_img, rec_slot, sel[:, 1:], sig[:, None], idx[:, None].float()], dim=1)
+        state.update(rois=rois, levels=levels, rec=rec, probs=cls["probs"], mask_feat=mask_feat, sel=sel)
+        return rec
+
+    def gather(rec):
+        # N > 1: the one collective of the path -- NCCL all-gather of the fixed-size records
         if world > 1:
-            rec, cnt = all_gather_records(rec, cnt)
-        state.update(rois=rois, levels=levels, rec=rec, cnt=cnt, probs=cls["probs"], mask_feat=mask_feat, sel=sel)
-        return rec, cnt
+            return all_gather_records(rec, cnt_words, sizes=[B_IMG] * world)
+        return rec, cnt_words
+
+    class GraphedStep(object):
+        """The step captured once as a CUDA graph and replayed (static shapes, no host syncs)."""
+
+        def __init__(self, fn):
+            self.fn = fn
+            self.graph = None
+            self.out = None
+            if args.no_graph:
+                return
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    fn()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.out = fn()
+            self.graph = g
+
+        def __call__(self):
+            if self.graph is None:
+                return self.fn()
+            self.graph.replay()
+            return self.out
 
     def sync_all():
         torch.cuda.synchronize()
@@ -359,15 +399,16 @@ def run_gpu(args):
     E_d = E_h.to(dev)
     words_d = [w.to(dev) for w in words_h]
 
+    run_step = GraphedStep(lambda: step(cand_boxes, cand_scores, feats, E_d, words_d))
     for _ in range(args.warmup):
-        step(cand_boxes, cand_scores, feats, E_d, words_d)
+        gather(run_step())
     sync_all()
     sampler = ClockSampler(local)
     sampler.start()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     for _ in range(args.steps):
-        step(cand_boxes, cand_scores, feats, E_d, words_d)
+        gather(run_step())
     t1.record()
     sync_all()
     clocks = sampler.stop()
@@ -389,15 +430,22 @@ def run_gpu(args):
     rec_h = torch.empty((B_IMG * world, w_max, 8), dtype=torch.float32).pin_memory()
     cnt_h = torch.empty((B_IMG * world,), dtype=torch.int32).pin_memory()
 
-    def step_e2e():
-        for d, s in zip(feats_e, feats_h):
-            d.copy_(s, non_blocking=True)
+    feats_e_view = [f.permute(0, 3, 1, 2) for f in feats_e]
+
+    def e2e_device_part():
+        for d, s_ in zip(feats_e, feats_h):
+            d.copy_(s_, non_blocking=True)
         cb_e.copy_(cand_boxes_h, non_blocking=True)
         cs_e.copy_(cand_scores_h, non_blocking=True)
         E_e.copy_(E_h, non_blocking=True)
-        for d, s in zip(words_e, words_h):
-            d.copy_(s, non_blocking=True)
-        rec, cnt = step(cb_e, cs_e, [f.permute(0, 3, 1, 2) for f in feats_e], E_e, words_e)
+        for d, s_ in zip(words_e, words_h):
+            d.copy_(s_, non_blocking=True)
+        return step(cb_e, cs_e, feats_e_view, E_e, words_e)
+
+    run_e2e = GraphedStep(e2e_device_part)
+
+    def step_e2e():
+        rec, cnt = gather(run_e2e())
         rec_h.copy_(rec, non_blocking=True)
         cnt_h.copy_(cnt, non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the caller holds the records on the host
@@ -447,7 +495,8 @@ def run_gpu(args):
                        "feature_layout": "channels_last (NHWC memory, logical [B,C,H,W])",
                        "roi_align_mode": "fma (<=1e-5 rel)" if args.fma else "exact (bit-identical to ROIAlign_cpu)",
                        "l2": "inputs (1.46 GB features/GPU) exceed the 126 MB L2; no flush needed",
-                       "images_per_sec": world * B_IMG / (ms_step * 1e-3)},
+                       "images_per_sec": world * B_IMG / (ms_step * 1e-3),
+                       "launch": "eager" if args.no_graph else "CUDA graph replay of the step (all-gather eager)"},
             "clocks": clocks,
             "e2e": {"value": rois_per_step / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(rec_h.numel() * 4 + cnt_h.numel() * 4) // world},
@@ -486,6 +535,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--fma", action="store_true", help="RoIAlign FMA mode (<=1e-5 rel) instead of bit-exact")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -31,6 +31,23 @@ inline int check_cuda(cudaError_t e, const char* what) {
     }                                           \
   } while (0)
 
+// Raise a kernel's dynamic shared-memory limit only when a launch needs more than any launch
+// before it (steady state issues no attribute calls, so steps can be captured in CUDA graphs).
+struct SmemHighWater {
+  size_t per_device[32] = {};  // the attribute is per device
+};
+template <typename K>
+inline int ensure_dynamic_smem(K kernel, size_t bytes, SmemHighWater* hw, const char* what) {
+  if (bytes <= 48 * 1024) return B200_OK;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  size_t& mark = hw->per_device[dev & 31];
+  if (bytes <= mark) return B200_OK;
+  int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes), what);
+  if (rc == B200_OK) mark = bytes;
+  return rc;
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 template <typename T>

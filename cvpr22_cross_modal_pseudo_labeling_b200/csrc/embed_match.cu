@@ -393,8 +393,8 @@ extern "C" int b200_embed_match(const void* A_bf16, const void* E_bf16, int64_t 
   if (rc != B200_OK) return rc;
   rc = make_map(&map_e, E_bf16, n_cols, dim, p.n_halves == 2 ? 256 : p.NP);
   if (rc != B200_OK) return rc;
-  rc = check_cuda(cudaFuncSetAttribute(embed_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                  "embed_match: smem attribute");
+  static SmemHighWater hw;
+  rc = ensure_dynamic_smem(embed_match_kernel, smem, &hw, "embed_match: smem attribute");
   if (rc != B200_OK) return rc;
   const long long grid = (n_rows + kBM - 1) / kBM;
   embed_match_kernel<<<(unsigned)grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(map_a, map_e, p);

@@ -551,16 +551,16 @@ extern "C" int b200_nms_batched(const float* boxes, const float* scores, const i
   if (fused_applies(max_seg_len, max_keep)) {
     if (max_seg_len <= 1024) {
       auto kern = nms_fused_kernel<256>;
-      int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                          "nms: cudaFuncSetAttribute");
+      static SmemHighWater hw;
+      int rc = ensure_dynamic_smem(kern, smem, &hw, "nms: cudaFuncSetAttribute");
       if (rc != B200_OK) return rc;
       kern<<<(unsigned)n_segments, 256, smem, st>>>(reinterpret_cast<const float4*>(boxes), scores, seg_offsets,
                                                     (int)max_seg_len, thresh, (long long)max_keep, n_cap, kl_cap,
                                                     w.order, reinterpret_cast<long long*>(keep_idx), keep_cnt);
     } else {
       auto kern = nms_fused_kernel<1024>;
-      int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                          "nms: cudaFuncSetAttribute");
+      static SmemHighWater hw;
+      int rc = ensure_dynamic_smem(kern, smem, &hw, "nms: cudaFuncSetAttribute");
       if (rc != B200_OK) return rc;
       kern<<<(unsigned)n_segments, 1024, smem, st>>>(reinterpret_cast<const float4*>(boxes), scores, seg_offsets,
                                                      (int)max_seg_len, thresh, (long long)max_keep, n_cap, kl_cap,

@@ -327,11 +327,9 @@ int launch_march(const LevelTable& lt, int C, const float* rois, int64_t n_rois,
                  int32_t* out_levels, cudaStream_t st) {
   const size_t smem = march_smem_bytes(PH * PW);
   auto kern = roi_align_fwd_march<kExact, kThreads, kMinBlocks>;
-  if (smem > 48 * 1024) {
-    int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                        "roi_align: smem attribute");
-    if (rc != B200_OK) return rc;
-  }
+  static SmemHighWater hw;  // one per template instantiation
+  int rc = ensure_dynamic_smem(kern, smem, &hw, "roi_align: smem attribute");
+  if (rc != B200_OK) return rc;
   const int64_t grid = n_rois * (C / kChunk);
   kern<<<(unsigned)grid, kThreads, smem, st>>>(lt, C, rois, PH, PW, out, out_levels);
   B200_CHECK_LAUNCH("roi_align_fwd_march");

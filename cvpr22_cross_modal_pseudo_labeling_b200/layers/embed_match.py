@@ -70,6 +70,53 @@ def embed_logits(cls_emb, E):
     return _EmbedLogits.apply(cls_emb, E)
 
 
+_plan_cache = {}
+
+
+def _align_plan(rows_per_image, wcounts, dev):
+    """Index tensors of caption_align for one (rows, words) signature, built once: groups of
+    consecutive images with at most MAX_COLS words, and per group the image id of every row /
+    word and the first row of every image.  Cached so that steady-state calls issue no host to
+    device copies (and can be captured in a CUDA graph)."""
+    key = (tuple(rows_per_image), tuple(wcounts), str(dev))
+    plan = _plan_cache.get(key)
+    if plan is not None:
+        return plan
+    nimg = len(rows_per_image)
+    row_start = [0]
+    for n in rows_per_image:
+        row_start.append(row_start[-1] + int(n))
+    groups, cur, cur_w = [], [], 0
+    for i in range(nimg):
+        w = wcounts[i]
+        if w > MAX_COLS:
+            raise ValueError("more than %d words in one caption" % MAX_COLS)
+        if cur and cur_w + w > MAX_COLS:
+            groups.append(cur)
+            cur, cur_w = [], 0
+        cur.append(i)
+        cur_w += w
+    if cur:
+        groups.append(cur)
+    plan = []
+    for g in groups:
+        wc = [wcounts[i] for i in g]
+        wt = sum(wc)
+        r0, r1 = row_start[g[0]], row_start[g[-1] + 1]
+        entry = dict(images=g, wc=wc, wt=wt, r0=r0, r1=r1)
+        if wt > 0 and r1 > r0:
+            ar = torch.arange(len(g), dtype=torch.int32, device=dev)
+            entry["row_seg"] = torch.repeat_interleave(ar, torch.tensor([rows_per_image[i] for i in g], device=dev),
+                                                       output_size=r1 - r0)
+            entry["col_seg"] = torch.repeat_interleave(ar, torch.tensor(wc, device=dev), output_size=wt)
+            entry["seg_start"] = torch.tensor([row_start[i] - r0 for i in g], dtype=torch.int32, device=dev)
+        plan.append(entry)
+    if len(_plan_cache) > 64:
+        _plan_cache.clear()
+    _plan_cache[key] = plan
+    return plan
+
+
 def caption_align(emb, rows_per_image, word_embs):
     """Caption-noun alignment for a batch (reference st_generalized_rcnn.py:243-255).
 
@@ -83,40 +130,17 @@ def caption_align(emb, rows_per_image, word_embs):
     assert len(word_embs) == nimg
     d = A.shape[1]
     results = [None] * nimg
-    row_start = [0]
-    for n in rows_per_image:
-        row_start.append(row_start[-1] + int(n))
-    # group consecutive images so that each call sees at most MAX_COLS words
-    groups, cur, cur_w = [], [], 0
-    for i in range(nimg):
-        w = int(word_embs[i].shape[0])
-        if w > MAX_COLS:
-            raise ValueError("more than %d words in one caption" % MAX_COLS)
-        if cur and cur_w + w > MAX_COLS:
-            groups.append(cur)
-            cur, cur_w = [], 0
-        cur.append(i)
-        cur_w += w
-    if cur:
-        groups.append(cur)
+    plan = _align_plan([int(n) for n in rows_per_image], [int(w.shape[0]) for w in word_embs], dev)
     lib = _ext.lib()
-    for g in groups:
-        wcounts = [int(word_embs[i].shape[0]) for i in g]
-        wt = sum(wcounts)
-        r0, r1 = row_start[g[0]], row_start[g[-1] + 1]
+    for e in plan:
+        g, wc, wt, r0, r1 = e["images"], e["wc"], e["wt"], e["r0"], e["r1"]
         if wt == 0 or r1 == r0:
-            for i in g:
-                w = int(word_embs[i].shape[0])
+            for i, w in zip(g, wc):
                 results[i] = (torch.full((w,), -1, dtype=torch.int64, device=dev),
                               torch.full((w,), float("-inf"), device=dev), torch.zeros((w,), device=dev))
             continue
-        E = torch.cat([_bf16(word_embs[i], "word_embs") for i in g if word_embs[i].shape[0] > 0], dim=0)
-        rcounts = torch.tensor([rows_per_image[i] for i in g], device=dev)
-        row_seg = torch.repeat_interleave(torch.arange(len(g), dtype=torch.int32, device=dev), rcounts,
-                                          output_size=r1 - r0)
-        col_seg = torch.repeat_interleave(torch.arange(len(g), dtype=torch.int32, device=dev),
-                                          torch.tensor(wcounts, device=dev), output_size=wt)
-        seg_start = torch.tensor([row_start[i] - r0 for i in g], dtype=torch.int32, device=dev)
+        parts = [_bf16(word_embs[i], "word_embs") for i in g if word_embs[i].shape[0] > 0]
+        E = parts[0] if len(parts) == 1 else torch.cat(parts, dim=0)
         best = torch.zeros((wt,), dtype=torch.int64, device=dev)   # uint64 keys
         ridx = torch.empty((wt,), dtype=torch.int32, device=dev)
         mx = torch.empty((wt,), dtype=torch.float32, device=dev)
@@ -124,14 +148,15 @@ def caption_align(emb, rows_per_image, word_embs):
         Ag = A[r0:r1]
         with torch.cuda.device(dev):
             rc = lib.b200_embed_match(_ext.ptr(Ag), _ext.ptr(E), r1 - r0, wt, d, _ext.B200_MATCH_COLMAX, 0.0,
-                                      None, None, None, None, _ext.ptr(row_seg), _ext.ptr(col_seg),
-                                      _ext.ptr(seg_start), _ext.ptr(best), _ext.stream_ptr(dev))
+                                      None, None, None, None, _ext.ptr(e["row_seg"]), _ext.ptr(e["col_seg"]),
+                                      _ext.ptr(e["seg_start"]), _ext.ptr(best), _ext.stream_ptr(dev))
             _ext.check(rc, "b200_embed_match")
             rc = lib.b200_colmax_decode(_ext.ptr(best), wt, _ext.ptr(ridx), _ext.ptr(mx), _ext.ptr(sg),
                                         _ext.stream_ptr(dev))
             _ext.check(rc, "b200_colmax_decode")
+        ridx64 = ridx.to(torch.int64)
         o = 0
-        for i, w in zip(g, wcounts):
-            results[i] = (ridx[o:o + w].to(torch.int64), mx[o:o + w], sg[o:o + w])
+        for i, w in zip(g, wc):
+            results[i] = (ridx64[o:o + w], mx[o:o + w], sg[o:o + w])
             o += w
     return results

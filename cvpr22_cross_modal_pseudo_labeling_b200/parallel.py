@@ -25,16 +25,25 @@ def shard_range(n_items, rank=None, world_size=None):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def all_gather_records(records, counts):
+def all_gather_records(records, counts, sizes=None):
     """records [B_local, W, 8] fp32, counts [B_local] int32 -> the same for ALL images, rank-major.
-    Shards may differ in size by one image; shorter shards are padded and trimmed after."""
+    Shards may differ in size by one image; shorter shards are padded and trimmed after.
+    `sizes` (images per rank) skips the size exchange and its host sync when the caller knows
+    the sharding (shard_range is deterministic)."""
     rank, ws = world()
     if ws == 1:
         return records, counts
-    n_local = torch.tensor([records.shape[0]], device=records.device, dtype=torch.int64)
-    sizes = [torch.zeros_like(n_local) for _ in range(ws)]
-    dist.all_gather(sizes, n_local)
-    sizes = [int(s.item()) for s in sizes]
+    if sizes is None:
+        n_local = torch.tensor([records.shape[0]], device=records.device, dtype=torch.int64)
+        sz = [torch.zeros_like(n_local) for _ in range(ws)]
+        dist.all_gather(sz, n_local)
+        sizes = [int(s.item()) for s in sz]
+    if len(set(sizes)) == 1:  # equal shards: no padding, two collectives, no sync
+        out_r = torch.empty((ws * sizes[0],) + tuple(records.shape[1:]), dtype=records.dtype, device=records.device)
+        out_c = torch.empty((ws * sizes[0],), dtype=counts.dtype, device=counts.device)
+        dist.all_gather_into_tensor(out_r, records.contiguous())
+        dist.all_gather_into_tensor(out_c, counts.contiguous())
+        return out_r, out_c
     n_max = max(sizes)
     pad_r = torch.zeros((n_max,) + tuple(records.shape[1:]), dtype=records.dtype, device=records.device)
     pad_c = torch.zeros((n_max,), dtype=counts.dtype, device=counts.device)
