@@ -176,24 +176,49 @@ struct AxisEntry {
 
 enum { kActReuse = 0, kActShift = 1, kActLoad2 = 2 };
 
+// V channels per lane (4 -> 128-bit loads, 2 -> 64-bit loads)
+template <int V>
+struct Vec {
+  float v[V];
+};
+
+template <int V>
+__device__ __forceinline__ Vec<V> ldg_vec(const float* p) {
+  Vec<V> r;
+  if (V == 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    r.v[0] = t.x; r.v[1] = t.y; r.v[V > 2 ? 2 : 0] = t.z; r.v[V > 3 ? 3 : 0] = t.w;
+  } else {
+    const float2 t = __ldg(reinterpret_cast<const float2*>(p));
+    r.v[0] = t.x; r.v[1] = t.y;
+  }
+  return r;
+}
+
 // rows[] / off are element offsets from `feat` (uniform across the CTA, < 2^31 per image)
-__device__ __forceinline__ void load_col(float4 (&dst)[4], const float* __restrict__ feat, const int (&rows)[4],
+template <int V>
+__device__ __forceinline__ void load_col(Vec<V> (&dst)[4], const float* __restrict__ feat, const int (&rows)[4],
                                          int off) {
 #pragma unroll
-  for (int k = 0; k < 4; ++k) dst[k] = __ldg(reinterpret_cast<const float4*>(feat + (unsigned)(rows[k] + off)));
+  for (int k = 0; k < 4; ++k) dst[k] = ldg_vec<V>(feat + (unsigned)(rows[k] + off));
 }
 
 // the two samples (iy = 0, 1) of one sample column: left taps in Lc, right taps in Rc
-template <bool kExact>
-__device__ __forceinline__ void sample_pair(const float4 (&Lc)[4], const float4 (&Rc)[4], const AxisEntry& ya,
-                                            const AxisEntry& yb, const AxisEntry& xt, float4& sa, float4& sb) {
-  sa = tap4v<kExact>(__fmul_rn(ya.h, xt.h), Lc[0], __fmul_rn(ya.h, xt.l), Rc[0], __fmul_rn(ya.l, xt.h), Lc[1],
-                     __fmul_rn(ya.l, xt.l), Rc[1]);
-  sb = tap4v<kExact>(__fmul_rn(yb.h, xt.h), Lc[2], __fmul_rn(yb.h, xt.l), Rc[2], __fmul_rn(yb.l, xt.h), Lc[3],
-                     __fmul_rn(yb.l, xt.l), Rc[3]);
+template <bool kExact, int V>
+__device__ __forceinline__ void sample_pair(const Vec<V> (&Lc)[4], const Vec<V> (&Rc)[4], const AxisEntry& ya,
+                                            const AxisEntry& yb, const AxisEntry& xt, Vec<V>& sa, Vec<V>& sb) {
+  const float a1 = __fmul_rn(ya.h, xt.h), a2 = __fmul_rn(ya.h, xt.l), a3 = __fmul_rn(ya.l, xt.h),
+              a4 = __fmul_rn(ya.l, xt.l);
+  const float b1 = __fmul_rn(yb.h, xt.h), b2 = __fmul_rn(yb.h, xt.l), b3 = __fmul_rn(yb.l, xt.h),
+              b4 = __fmul_rn(yb.l, xt.l);
+#pragma unroll
+  for (int c = 0; c < V; ++c) {
+    sa.v[c] = tap4<kExact>(a1, Lc[0].v[c], a2, Rc[0].v[c], a3, Lc[1].v[c], a4, Rc[1].v[c]);
+    sb.v[c] = tap4<kExact>(b1, Lc[2].v[c], b2, Rc[2].v[c], b3, Lc[3].v[c], b4, Rc[3].v[c]);
+  }
 }
 
-template <bool kExact, int kThreads, int kMinBlocks>
+template <bool kExact, int kThreads, int kMinBlocks, int V>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 roi_align_fwd_march(const LevelTable lt, int C, const float* __restrict__ rois, int PH, int PW,
                     float* __restrict__ out, int32_t* __restrict__ out_levels) {
@@ -254,57 +279,58 @@ roi_align_fwd_march(const LevelTable lt, int C, const float* __restrict__ rois, 
   }
   __syncthreads();
 
-  constexpr int kQuads = kChunk / 4;
+  constexpr int kGroups = kChunk / V;  // lane groups (V channels each) across the chunk
   const float* feat = lt.data[h.level] + (size_t)h.batch * H * W * C + c_begin;
-  // ---- march: thread = (output row ph, channel quad q) ----------------------------------
-  // Lane layout.  kThreads == 128 (PH <= 8): a warp owns 4 channel quads for ALL output rows
-  // (lane = ph * 4 + quad), so the sectors a warp reads are read by no other warp of the CTA
-  // and rows shared by neighbouring output rows are requested by the same warp back to back.
-  // kThreads == 256 (PH <= 16): 16 quads x 2 output rows per warp (full 256 B per pixel and
-  // request; measured faster than 2 quads x 16 rows for the 14x14 pooler).
-  constexpr int kLQ = kThreads == 128 ? 4 : 16;  // quads side by side in a warp
-  constexpr int kQGroups = kQuads / kLQ;         // warps needed to cover the 16 quads
+  // ---- march: thread = (output row ph, channel group q) ---------------------------------
+  // Lane layout.  PH <= 8: a warp owns 4 channel groups for ALL output rows (lane = ph * 4 +
+  // group), so the sectors a warp reads are read by no other warp of the CTA and rows shared
+  // by neighbouring output rows are requested by the same warp back to back.
+  // PH <= 16 (256 threads, V = 4): 16 groups x 2 output rows per warp (256 B per pixel and
+  // request; measured faster than 2 groups x 16 rows for the 14x14 pooler).
+  constexpr int kWarps = kThreads / 32;
+  constexpr int kLQ = kGroups / kWarps >= 4 ? 4 : 16;  // groups side by side in a warp
+  constexpr int kQGroups = kGroups / kLQ;              // warps needed to cover all groups
   {
     const int q = (warp % kQGroups) * kLQ + (lane % kLQ);
     const int ph = lane / kLQ + (32 / kLQ) * (warp / kQGroups);
     if (ph < PH) {
-    const AxisEntry ya = ytab[2 * ph], yb = ytab[2 * ph + 1];
-    const int rows[4] = {ya.lo + 4 * q, ya.hi + 4 * q, yb.lo + 4 * q, yb.hi + 4 * q};
-    // Two register columns (4 tap rows x 4 channels each) ping-pong between the roles
-    // "left tap" and "right tap": when the next sample's left column is the current right
-    // one, the roles swap and only one new column is loaded -- no register moves.
-    float4 A[4], B[4];
-    int a_is_left = 1;
-    float* o = out_s + (size_t)(4 * q) * NB + ph * PW;
-    for (int pw = 0; pw < PW; ++pw) {
-      float4 sa[2], sb[2];
+      const AxisEntry ya = ytab[2 * ph], yb = ytab[2 * ph + 1];
+      const int rows[4] = {ya.lo + V * q, ya.hi + V * q, yb.lo + V * q, yb.hi + V * q};
+      // Two register columns (4 tap rows x V channels each) ping-pong between the roles
+      // "left tap" and "right tap": when the next sample's left column is the current right
+      // one, the roles swap and only one new column is loaded -- no register moves.
+      Vec<V> A[4], B[4];
+      int a_is_left = 1;
+      float* o = out_s + (size_t)(V * q) * NB + ph * PW;
+      for (int pw = 0; pw < PW; ++pw) {
+        Vec<V> sa[2], sb[2];
 #pragma unroll
-      for (int ix = 0; ix < 2; ++ix) {
-        const AxisEntry xt = xtab[2 * pw + ix];
-        const int act = xt.lo & 3, xlo = xt.lo & ~3;
-        if (act == kActShift) {
-          a_is_left ^= 1;
-          if (a_is_left) load_col(B, feat, rows, xt.hi);
-          else load_col(A, feat, rows, xt.hi);
-        } else if (act == kActLoad2) {
-          if (a_is_left) {
-            load_col(A, feat, rows, xlo);
-            load_col(B, feat, rows, xt.hi);
-          } else {
-            load_col(B, feat, rows, xlo);
-            load_col(A, feat, rows, xt.hi);
+        for (int ix = 0; ix < 2; ++ix) {
+          const AxisEntry xt = xtab[2 * pw + ix];
+          const int act = xt.lo & 3, xlo = xt.lo & ~3;
+          if (act == kActShift) {
+            a_is_left ^= 1;
+            if (a_is_left) load_col<V>(B, feat, rows, xt.hi);
+            else load_col<V>(A, feat, rows, xt.hi);
+          } else if (act == kActLoad2) {
+            if (a_is_left) {
+              load_col<V>(A, feat, rows, xlo);
+              load_col<V>(B, feat, rows, xt.hi);
+            } else {
+              load_col<V>(B, feat, rows, xlo);
+              load_col<V>(A, feat, rows, xt.hi);
+            }
           }
+          if (a_is_left) sample_pair<kExact, V>(A, B, ya, yb, xt, sa[ix], sb[ix]);
+          else sample_pair<kExact, V>(B, A, ya, yb, xt, sa[ix], sb[ix]);
         }
-        if (a_is_left) sample_pair<kExact>(A, B, ya, yb, xt, sa[ix], sb[ix]);
-        else sample_pair<kExact>(B, A, ya, yb, xt, sa[ix], sb[ix]);
+        // (iy, ix) accumulation order of the reference, then / count (count = 4, exact)
+#pragma unroll
+        for (int c = 0; c < V; ++c) {
+          const float acc = __fadd_rn(__fadd_rn(__fadd_rn(sa[0].v[c], sa[1].v[c]), sb[0].v[c]), sb[1].v[c]);
+          o[c * NB + pw] = acc * 0.25f;
+        }
       }
-      // (iy, ix) accumulation order of the reference, then / count (count = 4, exact)
-      const float4 acc = add4(add4(add4(sa[0], sa[1]), sb[0]), sb[1]);
-      o[pw] = acc.x * 0.25f;
-      o[NB + pw] = acc.y * 0.25f;
-      o[2 * NB + pw] = acc.z * 0.25f;
-      o[3 * NB + pw] = acc.w * 0.25f;
-    }
     }
   }
   __syncthreads();
@@ -322,11 +348,11 @@ bool g_force_generic = false;
 bool g_exact = true;
 int g_variant = 0;  // tuning hook: occupancy variant of the marching kernel
 
-template <bool kExact, int kThreads, int kMinBlocks>
+template <bool kExact, int kThreads, int kMinBlocks, int V>
 int launch_march(const LevelTable& lt, int C, const float* rois, int64_t n_rois, int PH, int PW, float* out,
                  int32_t* out_levels, cudaStream_t st) {
   const size_t smem = march_smem_bytes(PH * PW);
-  auto kern = roi_align_fwd_march<kExact, kThreads, kMinBlocks>;
+  auto kern = roi_align_fwd_march<kExact, kThreads, kMinBlocks, V>;
   static SmemHighWater hw;  // one per template instantiation
   int rc = ensure_dynamic_smem(kern, smem, &hw, "roi_align: smem attribute");
   if (rc != B200_OK) return rc;
@@ -344,14 +370,15 @@ int launch_forward(const LevelTable& lt, int layout, int C, const float* rois, i
                         C % kChunk == 0 && (NB * kChunk) % 4 == 0;
   B200_REQUIRE(n_rois * ((C + 15) / 16) < (int64_t)1 << 31, "roi_align: too many RoIs for one launch");
   if (march_ok) {
-    // g_variant (tuning hook): CTAs/SM = 6 (default) / 5 / 4 for 128 threads, 3 / 3 / 2 for 256
+    // g_variant (tuning hook): CTAs/SM = 6 (default) / 5 / 4 for 128 threads, 3 / 3 / 2 for 256.
+    // (2 channels per lane with twice the warps was measured 35-55 % slower: V stays 4.)
     if (PH * (kChunk / 4) <= 128) {
-      if (g_variant == 1) return launch_march<kExact, 128, 5>(lt, C, rois, n_rois, PH, PW, out, out_levels, st);
-      if (g_variant == 2) return launch_march<kExact, 128, 4>(lt, C, rois, n_rois, PH, PW, out, out_levels, st);
-      return launch_march<kExact, 128, 6>(lt, C, rois, n_rois, PH, PW, out, out_levels, st);
+      if (g_variant == 1) return launch_march<kExact, 128, 5, 4>(lt, C, rois, n_rois, PH, PW, out, out_levels, st);
+      if (g_variant == 2) return launch_march<kExact, 128, 4, 4>(lt, C, rois, n_rois, PH, PW, out, out_levels, st);
+      return launch_march<kExact, 128, 6, 4>(lt, C, rois, n_rois, PH, PW, out, out_levels, st);
     }
-    if (g_variant == 2) return launch_march<kExact, 256, 2>(lt, C, rois, n_rois, PH, PW, out, out_levels, st);
-    return launch_march<kExact, 256, 3>(lt, C, rois, n_rois, PH, PW, out, out_levels, st);
+    if (g_variant == 2) return launch_march<kExact, 256, 2, 4>(lt, C, rois, n_rois, PH, PW, out, out_levels, st);
+    return launch_march<kExact, 256, 3, 4>(lt, C, rois, n_rois, PH, PW, out, out_levels, st);
   }
   // generic: pick channels per CTA so that a CTA has >= ~2k units of work
   int c_per_cta = C;
