@@ -197,33 +197,32 @@ embed_match_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     float v[16];
 
     if (p.mode == B200_MATCH_SOFTMAX) {
-      // pass 1: row max (over all N columns) and best foreground column (>= 1)
-      float mx = -INFINITY, best = -INFINITY;
+      // pass 1 (online softmax): running row max, rescaled exp-sum, best foreground column (>= 1)
+      float mx = -INFINITY, best = -INFINITY, sum = 0.f;
       int best_c = 0;
       for (int c0 = 0; c0 < N; c0 += 16) {
         tmem_ld16(taddr + c0, v);
+        float cmx = mx;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int c = c0 + i;
           if (c < N) {
-            mx = fmaxf(mx, v[i]);
+            cmx = fmaxf(cmx, v[i]);
             if (c >= 1 && v[i] > best) {
               best = v[i];
               best_c = c;
             }
           }
         }
-      }
-      // pass 2: normaliser
-      float sum = 0.f;
-      for (int c0 = 0; c0 < N; c0 += 16) {
-        tmem_ld16(taddr + c0, v);
+        float part = 0.f;
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-          if (c0 + i < N) sum += __expf(v[i] - mx);
+          if (c0 + i < N) part += __expf(v[i] - cmx);
+        sum = sum * __expf(mx - cmx) + part;  // exp(-inf) = 0 on the first chunk
+        mx = cmx;
       }
       const float inv = 1.0f / sum;
-      // pass 3: outputs
+      // pass 2: outputs
       if (p.probs || p.logits) {
         for (int c0 = 0; c0 < N; c0 += 16) {
           tmem_ld16(taddr + c0, v);
@@ -380,8 +379,9 @@ extern "C" int b200_embed_match(const void* A_bf16, const void* E_bf16, int64_t 
   p.col_best = reinterpret_cast<unsigned long long*>(col_best);
   const size_t stage_bytes = (size_t)kBM * kBK * 2 + (size_t)p.b_rows * kBK * 2;
   const int num_kb = (dim + kBK - 1) / kBK;
-  // ring depth: aim at ~100 KB per CTA so two CTAs share an SM when the E tile is small
-  int stages = (int)((100 * 1024) / stage_bytes);
+  // ring depth: ~52 KB per CTA when the E tile is small (N <= 128: four CTAs and their 128
+  // TMEM columns share an SM, so one tile's epilogue overlaps the others' loads), else ~100 KB
+  int stages = (int)(((p.tmem_cols <= 128 ? 52 : 100) * 1024) / stage_bytes);
   if (stages < 2) stages = 2;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages > num_kb) stages = num_kb < 1 ? 1 : num_kb;

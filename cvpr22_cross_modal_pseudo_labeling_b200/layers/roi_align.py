@@ -77,6 +77,7 @@ def _backward(grad_out, rois, shapes, layouts_nhwc, scales, output_size, samplin
     format of the forward input."""
     ph, pw = output_size
     grad_out = grad_out.float().contiguous()
+    rois = rois.float().contiguous()
     dev = grad_out.device
     fmt = torch.channels_last if layouts_nhwc else torch.contiguous_format
     grads = [torch.zeros(s, dtype=torch.float32, device=dev).contiguous(memory_format=fmt) for s in shapes]
