@@ -61,6 +61,9 @@ def lib():
         if hasattr(l, "b200_debug_set"):
             l.b200_debug_set.restype = None
             l.b200_debug_set.argtypes = [_i, _i, _i]
+        if hasattr(l, "b200_debug_bwd"):
+            l.b200_debug_bwd.restype = None
+            l.b200_debug_bwd.argtypes = [_i]
         if hasattr(l, "b200_debug_nms"):
             l.b200_debug_nms.restype = None
             l.b200_debug_nms.argtypes = [_i]
@@ -101,3 +104,8 @@ def debug_nms(force_bitmask=False):
     """Test hook: force the three-kernel bitmask NMS path (default: fused kernel when the
     longest segment fits in shared memory)."""
     lib().b200_debug_nms(int(force_bitmask))
+
+
+def debug_bwd(force_generic=False):
+    """Test hook: force the per-tap RoIAlign backward instead of the marching kernel."""
+    lib().b200_debug_bwd(int(force_generic))

@@ -26,7 +26,6 @@ namespace b200 {
 namespace {
 
 constexpr int kChunk = 64;        // channels per CTA in the staged kernel
-constexpr int kMaxAxisSamples = 32;
 
 template <bool kExact>
 __device__ __forceinline__ float tap4(float w1, float v1, float w2, float v2, float w3, float v3, float w4,
@@ -169,13 +168,6 @@ roi_align_fwd_generic(const LevelTable lt, int C, const float* __restrict__ rois
 // One CTA per (RoI, 64-channel chunk); shared memory holds only the two axis tables and
 // the [64 x NB] output tile, so many CTAs share an SM and the RoI's patch lives in L1.
 // ---------------------------------------------------------------------------------------
-struct AxisEntry {
-  int lo, hi;  // element offsets: y*W*C for the row table, x*C (| column action) for the column table
-  float l, h;
-};
-
-enum { kActReuse = 0, kActShift = 1, kActLoad2 = 2 };
-
 // V channels per lane (4 -> 128-bit loads, 2 -> 64-bit loads)
 template <int V>
 struct Vec {
@@ -243,40 +235,8 @@ roi_align_fwd_march(const LevelTable lt, int C, const float* __restrict__ rois, 
   const int H = lt.H[h.level], W = lt.W[h.level];
   const RoiGeom g = roi_geometry(h.x1, h.y1, h.x2, h.y2, lt.scale[h.level], PH, PW, 2);
 
-  // ---- axis tables: warp 0 -> y samples, warp 1 -> x samples ---------------------------
   const int warp = tid >> 5, lane = tid & 31;
-  if (warp < 2) {
-    const bool is_y = warp == 0;
-    const int ns = 2 * (is_y ? PH : PW);
-    bool ok = false;
-    AxisTap t;
-    t.lo = t.hi = 0;
-    t.l = t.h = 0.f;
-    if (lane < ns)
-      t = is_y ? axis_sample(g.start_h, lane >> 1, g.bin_h, lane & 1, 2, H, ok)
-               : axis_sample(g.start_w, lane >> 1, g.bin_w, lane & 1, 2, W, ok);
-    ok = ok && lane < ns;
-    {
-      AxisEntry e;
-      const int stride = is_y ? W * C : C;
-      // an out-of-range sample contributes nothing (ROIAlign_cpu.cpp:47-61): zero weights,
-      // taps parked on element 0 of the axis
-      e.lo = ok ? t.lo * stride : 0;
-      e.hi = ok ? t.hi * stride : 0;
-      e.l = ok ? t.l : 0.f;
-      e.h = ok ? t.h : 0.f;
-      // what the x-march must do to have (lo, hi) in its two register columns, given the
-      // previous sample's columns.  C % 64 == 0 leaves the low bits of `lo` free for it.
-      const int plo = __shfl_up_sync(0xffffffffu, e.lo, 1), phi = __shfl_up_sync(0xffffffffu, e.hi, 1);
-      int act = kActLoad2;
-      if (lane > 0) {
-        if (e.lo == plo && e.hi == phi) act = kActReuse;
-        else if (e.lo == phi) act = kActShift;
-      }
-      if (!is_y) e.lo |= act;
-      if (lane < ns) (is_y ? ytab : xtab)[lane] = e;
-    }
-  }
+  build_axis_tables(g, PH, PW, H, W, C, warp, lane, ytab, xtab);
   __syncthreads();
 
   constexpr int kGroups = kChunk / V;  // lane groups (V channels each) across the chunk

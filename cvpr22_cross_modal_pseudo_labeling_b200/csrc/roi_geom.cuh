@@ -88,4 +88,51 @@ __device__ __forceinline__ AxisTap axis_sample(float start, int p, float bin, in
   return t;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Per-RoI axis tables of the marching kernels (sampling_ratio 2, NHWC).
+// ---------------------------------------------------------------------------------------
+struct AxisEntry {
+  int lo, hi;  // element offsets: y*W*C for the row table, x*C (| column action) for the column table
+  float l, h;
+};
+
+enum { kActReuse = 0, kActShift = 1, kActLoad2 = 2 };
+constexpr int kMaxAxisSamples = 32;
+
+// warp 0 fills the 2*PH row entries, warp 1 the 2*PW column entries (PH, PW <= 16); the caller
+// synchronises the CTA afterwards.
+__device__ __forceinline__ void build_axis_tables(const RoiGeom& g, int PH, int PW, int H, int W, int C, int warp,
+                                                  int lane, AxisEntry* ytab, AxisEntry* xtab) {
+  if (warp >= 2) return;
+  const bool is_y = warp == 0;
+  const int ns = 2 * (is_y ? PH : PW);
+  bool ok = false;
+  AxisTap t;
+  t.lo = t.hi = 0;
+  t.l = t.h = 0.f;
+  if (lane < ns)
+    t = is_y ? axis_sample(g.start_h, lane >> 1, g.bin_h, lane & 1, 2, H, ok)
+             : axis_sample(g.start_w, lane >> 1, g.bin_w, lane & 1, 2, W, ok);
+  ok = ok && lane < ns;
+  AxisEntry e;
+  const int stride = is_y ? W * C : C;
+  // an out-of-range sample contributes nothing (ROIAlign_cpu.cpp:47-61): zero weights, taps
+  // parked on element 0 of the axis
+  e.lo = ok ? t.lo * stride : 0;
+  e.hi = ok ? t.hi * stride : 0;
+  e.l = ok ? t.l : 0.f;
+  e.h = ok ? t.h : 0.f;
+  // what the x-march must do to have (lo, hi) in its two register columns, given the previous
+  // sample's columns.  C % 64 == 0 leaves the low bits of `lo` free for it.
+  const int plo = __shfl_up_sync(0xffffffffu, e.lo, 1), phi = __shfl_up_sync(0xffffffffu, e.hi, 1);
+  int act = kActLoad2;
+  if (lane > 0) {
+    if (e.lo == plo && e.hi == phi) act = kActReuse;
+    else if (e.lo == phi) act = kActShift;
+  }
+  if (!is_y) e.lo |= act;
+  if (lane < ns) (is_y ? ytab : xtab)[lane] = e;
+}
+
 }  // namespace b200

@@ -80,7 +80,7 @@ def _backward(grad_out, rois, shapes, layouts_nhwc, scales, output_size, samplin
     rois = rois.float().contiguous()
     dev = grad_out.device
     fmt = torch.channels_last if layouts_nhwc else torch.contiguous_format
-    grads = [torch.zeros(s, dtype=torch.float32, device=dev).contiguous(memory_format=fmt) for s in shapes]
+    grads = [torch.empty(s, dtype=torch.float32, device=dev, memory_format=fmt).zero_() for s in shapes]
     r = rois.size(0)
     if r > 0:
         arr = _levels_array(grads, scales)

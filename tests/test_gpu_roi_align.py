@@ -130,9 +130,17 @@ def test_pooler_multilevel_matches_oracle(nhwc, res):
     assert np.array_equal(got.cpu().numpy(), want)
 
 
+@pytest.fixture(params=["march", "generic"])
+def bwd_path(request):
+    """Backward runs on the marching kernel (NHWC, sampling_ratio 2) and on the per-tap kernel."""
+    _ext().debug_bwd(request.param == "generic")
+    yield request.param
+    _ext().debug_bwd(False)
+
+
 @pytest.mark.parametrize("nhwc", [False, True])
 @pytest.mark.parametrize("cfg", [(7, 7, 2), (14, 14, 2), (5, 3, 0)])
-def test_roi_align_backward(nhwc, cfg):
+def test_roi_align_backward(nhwc, cfg, bwd_path):
     from cvpr22_cross_modal_pseudo_labeling_b200.layers import roi_align
     ph, pw, sr = cfg
     rng = np.random.default_rng(23 + ph)
@@ -150,7 +158,7 @@ def test_roi_align_backward(nhwc, cfg):
     assert (want64 != 0).any()
 
 
-def test_pooler_backward_multilevel():
+def test_pooler_backward_multilevel(bwd_path):
     from cvpr22_cross_modal_pseudo_labeling_b200.modeling import Pooler
     from cvpr22_cross_modal_pseudo_labeling_b200.structures import BoxList
     rng = np.random.default_rng(29)
