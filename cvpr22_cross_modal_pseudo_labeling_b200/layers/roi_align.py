@@ -1,6 +1,7 @@
 """RoIAlign entry points mirroring maskrcnn_benchmark.layers.roi_align (reference
 layers/roi_align.py:12-61) plus the fused multi-level form the Pooler uses."""
 import ctypes
+import weakref
 
 import torch
 from torch import nn
@@ -93,21 +94,63 @@ def _backward(grad_out, rois, shapes, layouts_nhwc, scales, output_size, samplin
     return grads
 
 
+class _NhwcCache(object):
+    """NCHW-contiguous feature maps are re-laid out to NHWC once per tensor (b200_nchw_to_nhwc)
+    and reused by every pooler call that sees the same tensor object at the same version: the
+    box pooler, the mask pooler, and the backward pass."""
+
+    def __init__(self, capacity=16):
+        self.capacity = capacity
+        self.entries = {}
+
+    def get(self, x):
+        key = id(x)
+        e = self.entries.get(key)
+        if e is not None:
+            ref, version, y = e
+            if ref() is x and x._version == version:
+                return y
+        b, c, h, w = x.shape
+        src = x.detach()
+        y = torch.empty((b, c, h, w), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+        with torch.cuda.device(x.device):
+            rc = _ext.lib().b200_nchw_to_nhwc(_ext.ptr(src), _ext.ptr(y), b, c, h, w, _ext.stream_ptr(x.device))
+        _ext.check(rc, "b200_nchw_to_nhwc")
+        if len(self.entries) >= self.capacity:
+            self.entries.clear()
+        self.entries[key] = (weakref.ref(x), x._version, y)
+        return y
+
+
+nhwc_cache = _NhwcCache()
+
+
+def _stageable(f, sampling_ratio):
+    """NCHW-contiguous CUDA map that the marching kernels could take if it were NHWC."""
+    return (f.is_cuda and f.dim() == 4 and sampling_ratio == 2 and f.size(1) % 64 == 0 and f.size(1) > 1 and
+            f.is_contiguous() and not f.is_contiguous(memory_format=torch.channels_last))
+
+
 class _ROIAlignMulti(Function):
     """Fused level-assignment + RoIAlign over a feature pyramid (reference
-    modeling/poolers.py:91-121 + layers/roi_align.py:12-45)."""
+    modeling/poolers.py:91-121 + layers/roi_align.py:12-45).  With `stage`, NCHW-contiguous
+    maps run through a cached NHWC copy (forward) and an NHWC gradient buffer that is laid
+    back out to NCHW (backward), so both directions use the marching kernels."""
 
     @staticmethod
-    def forward(ctx, rois, output_size, scales, sampling_ratio, *feats):
+    def forward(ctx, rois, output_size, scales, sampling_ratio, stage, *feats):
         output_size = _pair(output_size)
-        out, _ = _forward(list(feats), scales, rois, output_size, sampling_ratio)
+        staged = [bool(stage) and _stageable(f, sampling_ratio) for f in feats]
+        run = [nhwc_cache.get(f) if s else f for f, s in zip(feats, staged)]
+        out, _ = _forward(run, scales, rois, output_size, sampling_ratio)
         ctx.save_for_backward(rois.float().contiguous())
         ctx.output_size = output_size
         ctx.scales = tuple(scales)
         ctx.sampling_ratio = sampling_ratio
         ctx.shapes = [tuple(f.shape) for f in feats]
-        lay = {_layout_of(f)[0] for f in feats}
+        lay = {_layout_of(f)[0] for f in run}
         ctx.nhwc = lay == {_ext.B200_LAYOUT_NHWC}
+        ctx.staged = staged
         return out
 
     @staticmethod
@@ -116,17 +159,32 @@ class _ROIAlignMulti(Function):
         (rois,) = ctx.saved_tensors
         grads = _backward(grad_output, rois, ctx.shapes, ctx.nhwc, ctx.scales, ctx.output_size,
                           ctx.sampling_ratio)
-        return (None, None, None, None, *grads)
+        if ctx.nhwc and any(ctx.staged):
+            # the caller's maps are NCHW-contiguous: hand back gradients in that layout
+            lib = _ext.lib()
+            out = []
+            for g, s in zip(grads, ctx.staged):
+                if s:
+                    b, c, h, w = g.shape
+                    n = torch.empty((b, c, h, w), dtype=g.dtype, device=g.device)
+                    with torch.cuda.device(g.device):
+                        rc = lib.b200_nhwc_to_nchw(_ext.ptr(g), _ext.ptr(n), b, c, h, w, _ext.stream_ptr(g.device))
+                    _ext.check(rc, "b200_nhwc_to_nchw")
+                    g = n
+                out.append(g)
+            grads = out
+        return (None, None, None, None, None, *grads)
 
 
-def roi_align_multilevel(feats, rois, output_size, scales, sampling_ratio):
-    """feats: list of [B,C,H_l,W_l]; rois [R,5] -> [R,C,PH,PW] in RoI order."""
-    return _ROIAlignMulti.apply(rois, output_size, tuple(scales), sampling_ratio, *feats)
+def roi_align_multilevel(feats, rois, output_size, scales, sampling_ratio, stage_nhwc=False):
+    """feats: list of [B,C,H_l,W_l]; rois [R,5] -> [R,C,PH,PW] in RoI order.
+    stage_nhwc: run NCHW-contiguous maps through a cached NHWC copy (see _ROIAlignMulti)."""
+    return _ROIAlignMulti.apply(rois, output_size, tuple(scales), sampling_ratio, stage_nhwc, *feats)
 
 
 def roi_align(input, roi, output_size, spatial_scale, sampling_ratio):
     """Same call as the reference's `roi_align = _ROIAlign.apply` (layers/roi_align.py:48)."""
-    return _ROIAlignMulti.apply(roi, output_size, (spatial_scale,), sampling_ratio, input)
+    return _ROIAlignMulti.apply(roi, output_size, (spatial_scale,), sampling_ratio, False, input)
 
 
 class ROIAlign(nn.Module):

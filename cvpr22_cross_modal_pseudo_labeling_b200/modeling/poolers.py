@@ -5,8 +5,6 @@ call signature, but the level assignment (LevelMapper, :31-42), the per-level
 RoIAlign launches and the scatter back (:111-119) are ONE kernel launch
 (b200_roi_align_forward), with autograd through b200_roi_align_backward.
 """
-import weakref
-
 import torch
 from torch import nn
 
@@ -32,42 +30,14 @@ class LevelMapper(object):
         return lv.to(torch.int64) - self.k_min
 
 
-class _NhwcCache(object):
-    """NCHW-contiguous feature maps are re-laid out to NHWC once per tensor and reused by
-    every pooler that sees the same tensor (box 7x7, mask 14x14, forward and backward)."""
-
-    def __init__(self, capacity=16):
-        self.capacity = capacity
-        self.entries = {}
-
-    def get(self, x):
-        key = id(x)
-        e = self.entries.get(key)
-        if e is not None:
-            ref, version, y = e
-            if ref() is x and x._version == version:
-                return y
-        b, c, h, w = x.shape
-        y = torch.empty((b, c, h, w), dtype=x.dtype, device=x.device).contiguous(memory_format=torch.channels_last)
-        with torch.cuda.device(x.device):
-            rc = _ext.lib().b200_nchw_to_nhwc(_ext.ptr(x), _ext.ptr(y), b, c, h, w, _ext.stream_ptr(x.device))
-        _ext.check(rc, "b200_nchw_to_nhwc")
-        if len(self.entries) >= self.capacity:
-            self.entries.clear()
-        self.entries[key] = (weakref.ref(x), x._version, y)
-        return y
-
-
-_nhwc_cache = _NhwcCache()
-
-
 class Pooler(nn.Module):
     def __init__(self, output_size, scales, sampling_ratio, stage_nhwc=True):
         """
         output_size (tuple[int] or int), scales (list[float]), sampling_ratio (int):
         as the reference (poolers.py:55-76).
-        stage_nhwc: re-lay NCHW-contiguous inference inputs out to NHWC (cached per tensor)
-        so the staged kernel runs; channels_last inputs are always used in place.
+        stage_nhwc: run NCHW-contiguous maps through an NHWC copy cached per tensor (and an NHWC
+        gradient buffer laid back out to NCHW in the backward) so the marching kernels are used;
+        channels_last inputs are always used in place.
         """
         super(Pooler, self).__init__()
         self.poolers = nn.ModuleList(
@@ -92,16 +62,8 @@ class Pooler(nn.Module):
         """x: list[Tensor [B,C,H_l,W_l]], boxes: list[BoxList] -> [R,C,PH,PW] in RoI order."""
         rois = self.convert_to_roi_format(boxes)
         feats = list(x)[: len(self.scales)]
-        if self.stage_nhwc and self.sampling_ratio == 2 and feats[0].size(1) % 64 == 0:
-            staged = []
-            for f in feats:
-                needs_grad = f.requires_grad and torch.is_grad_enabled()
-                if f.is_cuda and f.is_contiguous() and not needs_grad and f.size(1) > 1 and \
-                        not f.is_contiguous(memory_format=torch.channels_last):
-                    f = _nhwc_cache.get(f)
-                staged.append(f)
-            feats = staged
-        return roi_align_multilevel(feats, rois, self.output_size, self.scales, self.sampling_ratio)
+        return roi_align_multilevel(feats, rois, self.output_size, self.scales, self.sampling_ratio,
+                                    stage_nhwc=self.stage_nhwc)
 
 
 def make_pooler(cfg, head_name):

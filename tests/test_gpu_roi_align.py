@@ -202,3 +202,36 @@ def test_roi_pool_matches_oracle():
     out.backward(torch.from_numpy(g).cuda())
     wg = oracle.roi_pool_backward(g, arg, rois, 7, 7, 2, 16, 30, 40)
     np.testing.assert_allclose(x.grad.cpu().numpy(), wg, rtol=1e-5, atol=1e-6)
+
+
+def test_pooler_nchw_training_path_is_staged_and_exact():
+    """NCHW-contiguous maps that require grad: the forward runs on the cached NHWC copy (still
+    bit-exact), the backward returns NCHW-contiguous gradients within tolerance."""
+    from cvpr22_cross_modal_pseudo_labeling_b200.layers.roi_align import nhwc_cache
+    from cvpr22_cross_modal_pseudo_labeling_b200.modeling import Pooler
+    from cvpr22_cross_modal_pseudo_labeling_b200.structures import BoxList
+    rng = np.random.default_rng(41)
+    b, c, n = 2, 64, 100
+    feats = [f.requires_grad_(True) for f in _pyramid(rng, b, c, False, 400, 672)]
+    rois = synth.make_rois(rng, n, b, 672, 400, smin=8, smax=400)
+    boxes = [BoxList(torch.from_numpy(rois[i * n:(i + 1) * n, 1:]).cuda(), (672, 400)) for i in range(b)]
+    pooler = Pooler((7, 7), synth.FPN_SCALES, 2)
+    out = pooler(feats, boxes)
+    assert any(e[0]() is feats[0] for e in nhwc_cache.entries.values())      # staged
+    want, _ = oracle.pooler_forward([f.detach().cpu().numpy() for f in feats], rois, synth.FPN_SCALES, 7, 7, 2)
+    assert np.array_equal(out.detach().cpu().numpy(), want)
+    g = rng.standard_normal(tuple(out.shape)).astype(np.float32)
+    out.backward(torch.from_numpy(g).cuda())
+    lv = oracle.level_map(rois, 2.0, 5.0)
+    for l, f in enumerate(feats):
+        assert f.grad.is_contiguous()
+        idx = np.nonzero(lv == l)[0]
+        _, w64 = oracle.roi_align_backward(g[idx], rois[idx], synth.FPN_SCALES[l], 7, 7, b, c, f.shape[2], f.shape[3], 2)
+        _, mag = oracle.roi_align_backward(np.abs(g[idx]), rois[idx], synth.FPN_SCALES[l], 7, 7, b, c, f.shape[2], f.shape[3], 2)
+        assert np.all(np.abs(f.grad.cpu().numpy() - w64) <= RTOL * mag + 1e-30), l
+    # an in-place update invalidates the cached copy
+    with torch.no_grad():
+        feats[0].mul_(2.0)
+    out2 = pooler(feats, boxes)
+    want2, _ = oracle.pooler_forward([f.detach().cpu().numpy() for f in feats], rois, synth.FPN_SCALES, 7, 7, 2)
+    assert np.array_equal(out2.detach().cpu().numpy(), want2)
