@@ -513,6 +513,82 @@ Workspace carve(void* base, int64_t n_total, int64_t n_segments, int64_t max_seg
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------
+// Cross-level proposal selection: per image, the top_n highest-scoring boxes among the boxes
+// its NMS segments kept (reference modeling/rpn/inference.py:173-180, select_over_all_levels
+// in test mode), emitted directly in RoI format (batch, x1, y1, x2, y2) for the pooler.
+// One CTA per image: gather (score, global index) keys of the kept boxes, bitonic sort in
+// shared memory, write the first top_n.  Equal scores keep ascending global index order.
+// ---------------------------------------------------------------------------------------
+constexpr int kSelectThreads = 1024;
+constexpr int kSelectMax = 16384;
+
+__global__ void __launch_bounds__(kSelectThreads)
+select_topk_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores,
+                   const int32_t* __restrict__ seg_off, const long long* __restrict__ keep_idx,
+                   const int32_t* __restrict__ keep_cnt, int segs_per_image, int top_n, int npad_max,
+                   float* __restrict__ rois_out, float* __restrict__ scores_out, int32_t* __restrict__ count_out) {
+  extern __shared__ u64 skeys[];
+  __shared__ int s_base[65];
+  const int img = blockIdx.x, tid = threadIdx.x;
+  const int s0 = img * segs_per_image;
+  if (tid == 0) {
+    int acc = 0;
+    for (int l = 0; l < segs_per_image; ++l) {
+      s_base[l] = acc;
+      acc += keep_cnt[s0 + l];
+    }
+    s_base[segs_per_image] = acc < npad_max ? acc : npad_max;
+  }
+  __syncthreads();
+  const int total = s_base[segs_per_image];
+  int npad = 2;
+  while (npad < total) npad <<= 1;
+  for (int i = tid; i < npad; i += kSelectThreads) skeys[i] = ~0ull;
+  __syncthreads();
+  for (int l = 0; l < segs_per_image; ++l) {
+    const int off = seg_off[s0 + l], base = s_base[l];
+    const int cnt = min(keep_cnt[s0 + l], total - base);
+    for (int j = tid; j < cnt; j += kSelectThreads) {
+      const int gi = off + (int)keep_idx[off + j];
+      skeys[base + j] = ((u64)desc_score_bits(scores[gi]) << 32) | (uint32_t)gi;
+    }
+  }
+  __syncthreads();
+  for (int k = 2; k <= npad; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = tid; t < (npad >> 1); t += kSelectThreads) {
+        const int lo = 2 * t - (t & (j - 1)), hi = lo + j;
+        const u64 a = skeys[lo], b = skeys[hi];
+        if ((a > b) == ((lo & k) == 0)) {
+          skeys[lo] = b;
+          skeys[hi] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  const int n_out = min(total, top_n);
+  for (int i = tid; i < top_n; i += kSelectThreads) {
+    float* r = rois_out + ((size_t)img * top_n + i) * 5;
+    if (i < n_out) {
+      const int gi = (int)(uint32_t)skeys[i];
+      const float4 b = boxes[gi];
+      r[0] = (float)img;
+      r[1] = b.x;
+      r[2] = b.y;
+      r[3] = b.z;
+      r[4] = b.w;
+      if (scores_out) scores_out[(size_t)img * top_n + i] = scores[gi];
+    } else {
+      r[0] = (float)img;
+      r[1] = r[2] = r[3] = r[4] = 0.f;
+      if (scores_out) scores_out[(size_t)img * top_n + i] = 0.f;
+    }
+  }
+  if (tid == 0) count_out[img] = n_out;
+}
+
 extern "C" void b200_debug_nms(int force_bitmask) { g_nms_force_bitmask = force_bitmask != 0; }
 
 extern "C" size_t b200_nms_workspace_bytes(int64_t n_total, int64_t n_segments, int64_t max_seg_len) {
@@ -592,5 +668,33 @@ extern "C" int b200_nms_batched(const float* boxes, const float* scores, const i
       w.mask, w.order, w.sorted_flag, seg_offsets, (int)max_seg_len, MB, (long long)max_keep,
       reinterpret_cast<long long*>(keep_idx), keep_cnt);
   B200_CHECK_LAUNCH("nms_sweep_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_select_topk(const float* boxes, const float* scores, const int32_t* seg_offsets,
+                                const int64_t* keep_idx, const int32_t* keep_cnt, int n_images, int segs_per_image,
+                                int64_t max_kept_per_image, int top_n, float* rois_out, float* scores_out,
+                                int32_t* count_out, void* stream) {
+  using namespace b200;
+  B200_REQUIRE(n_images >= 0 && segs_per_image >= 1 && segs_per_image <= 64 && top_n >= 1 && max_kept_per_image >= 0,
+               "select_topk: bad shape");
+  if (n_images == 0) return B200_OK;
+  B200_REQUIRE(boxes && scores && seg_offsets && keep_idx && keep_cnt && rois_out && count_out,
+               "select_topk: null pointer");
+  B200_REQUIRE(aligned16(boxes), "select_topk: boxes must be 16-byte aligned");
+  if (max_kept_per_image > kSelectMax) {
+    set_error("select_topk: %lld kept boxes per image exceed %d", (long long)max_kept_per_image, kSelectMax);
+    return B200_ERR_UNSUPPORTED;
+  }
+  int npad = 2;
+  while (npad < max_kept_per_image) npad <<= 1;
+  const size_t smem = sizeof(u64) * (size_t)npad;
+  static SmemHighWater hw;
+  int rc = ensure_dynamic_smem(select_topk_kernel, smem, &hw, "select_topk: smem attribute");
+  if (rc != B200_OK) return rc;
+  select_topk_kernel<<<n_images, kSelectThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(boxes), scores, seg_offsets, reinterpret_cast<const long long*>(keep_idx),
+      keep_cnt, segs_per_image, top_n, npad, rois_out, scores_out, count_out);
+  B200_CHECK_LAUNCH("select_topk_kernel");
   return B200_OK;
 }

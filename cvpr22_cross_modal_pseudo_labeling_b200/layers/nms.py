@@ -71,3 +71,23 @@ def nms(dets, scores, threshold):
     off = torch.tensor([0, n], dtype=torch.int32, device=dets.device)
     keep_idx, keep_cnt = nms_batched(dets, scores, off, threshold, -1, n)
     return keep_idx[: int(keep_cnt.item())]
+
+
+def select_topk(boxes, scores, seg_offsets, keep_idx, keep_cnt, n_images, top_n, max_kept_per_image):
+    """Per image, the top_n best boxes among those kept by `nms_batched` in the image's
+    consecutive segments (the RPN's cross-level selection, reference rpn/inference.py:173-180).
+    Returns (rois [n_images*top_n, 5], scores [n_images*top_n], count int32 [n_images]); no host sync."""
+    _ext.require_cuda(boxes, "boxes")
+    s = keep_cnt.numel()
+    if n_images <= 0 or s % n_images:
+        raise ValueError("segments must divide evenly among images")
+    dev = boxes.device
+    rois = torch.empty((n_images * top_n, 5), dtype=torch.float32, device=dev)
+    sc = torch.empty((n_images * top_n,), dtype=torch.float32, device=dev)
+    cnt = torch.empty((n_images,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _ext.lib().b200_select_topk(_ext.ptr(boxes), _ext.ptr(scores), _ext.ptr(seg_offsets), _ext.ptr(keep_idx),
+                                         _ext.ptr(keep_cnt), n_images, s // n_images, int(max_kept_per_image),
+                                         int(top_n), _ext.ptr(rois), _ext.ptr(sc), _ext.ptr(cnt), _ext.stream_ptr(dev))
+    _ext.check(rc, "b200_select_topk")
+    return rois, sc, cnt

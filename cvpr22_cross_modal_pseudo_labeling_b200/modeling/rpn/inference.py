@@ -4,7 +4,7 @@ instead of B x L calls of boxlist_nms (reference :111-122), and one host sync pe
 """
 import torch
 
-from ...layers import nms_batched
+from ...layers import nms_batched, select_topk
 from ...structures import BoxList, cat_boxlist
 from ..box_coder import BoxCoder
 
@@ -105,6 +105,27 @@ class RPNPostProcessor(torch.nn.Module):
             small = (w < self.min_size) | (h < self.min_size)
         else:
             small = None
+
+        fused_select = (self.nms_thresh > 0 and small is None and num_levels > 1 and
+                        not (self.training and self.fpn_post_nms_per_batch))
+        if fused_select:
+            per_img = sum(min(k, self.post_nms_top_n) if self.post_nms_top_n > 0 else k for k in ks)
+            fused_select = per_img <= 16384
+        if fused_select:
+            # NMS for all (image, level) segments, then the per-image top-k over levels
+            # (reference :173-180) in one more kernel; one host sync for the counts
+            keep_idx, keep_cnt = nms_batched(boxes, score, seg_off, self.nms_thresh, self.post_nms_top_n, max(ks))
+            k2 = min(self.fpn_post_nms_top_n, K)
+            rois, sc, cnt = select_topk(boxes, score, seg_off, keep_idx, keep_cnt, n_img, k2, per_img)
+            n_keep = cnt.tolist()
+            results = []
+            for i in range(n_img):
+                bl = BoxList(rois[i * k2:i * k2 + n_keep[i], 1:], sizes[i], mode="xyxy")
+                bl.add_field("objectness", sc[i * k2:i * k2 + n_keep[i]])
+                results.append(bl)
+            if self.training and targets is not None:
+                results = self.add_gt_proposals(results, targets)
+            return results
 
         if self.nms_thresh > 0:
             nms_scores = score

@@ -44,8 +44,7 @@ const char* b200_last_error_string(void);
  *   B200_LAYOUT_NCHW : contiguous as the reference requires
  *                      (csrc/cuda/ROIAlign_cuda.cu:286 `.contiguous()`).
  *   B200_LAYOUT_NHWC : torch.channels_last strides (memory [B, H, W, C]); the
- *                      fast path -- 128-bit channel-vector gathers staged in
- *                      shared memory by bulk async copies.
+ *                      fast path -- every tap is a 128-bit channel-vector load.
  * ------------------------------------------------------------------------ */
 #define B200_LAYOUT_NCHW 0
 #define B200_LAYOUT_NHWC 1
@@ -144,6 +143,24 @@ int b200_nms_batched(const float* boxes, const float* scores,
                      int64_t n_segments, int64_t max_seg_len, float thresh,
                      int64_t max_keep, int64_t* keep_idx, int32_t* keep_cnt,
                      void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Cross-level proposal selection after the batched NMS: per image, the top_n highest-scoring
+ * boxes among those its `segs_per_image` consecutive segments kept, written in RoI format.
+ * Replaces RPNPostProcessor.select_over_all_levels in test mode
+ * (modeling/rpn/inference.py:173-180) and the cat_boxlist / convert_to_roi_format glue that
+ * feeds the pooler (modeling/rpn/inference.py:145-146, modeling/poolers.py:78-89).
+ *   keep_idx / keep_cnt     outputs of b200_nms_batched over n_images * segs_per_image segments
+ *   max_kept_per_image      host upper bound on sum of keep_cnt per image (<= 16384)
+ *   rois_out  [n_images*top_n, 5] fp32 (image index, x1, y1, x2, y2), descending score per
+ *             image (equal scores: ascending box index); rows past count_out[i] are zero boxes
+ *   scores_out [n_images*top_n] fp32 (may be NULL), count_out [n_images] int32
+ */
+int b200_select_topk(const float* boxes, const float* scores,
+                     const int32_t* seg_offsets, const int64_t* keep_idx,
+                     const int32_t* keep_cnt, int n_images, int segs_per_image,
+                     int64_t max_kept_per_image, int top_n, float* rois_out,
+                     float* scores_out, int32_t* count_out, void* stream);
 
 /*
  * Region -> class-embedding scoring: logits = A . E^T on the tcgen05 tensor

@@ -132,3 +132,35 @@ def test_nms_full_size_properties():
     a, b = int(off[s]), int(off[s + 1])
     want = oracle.nms(boxes[a:b].cpu().numpy(), scores[a:b].cpu().numpy(), 0.7)
     assert np.array_equal(ki[a:a + int(kc_h[s])].cpu().numpy(), want)
+
+
+def test_select_topk_matches_numpy():
+    """Per-image cross-level top-k after the batched NMS (reference rpn/inference.py:173-180)."""
+    from cvpr22_cross_modal_pseudo_labeling_b200.layers import nms_batched, select_topk
+    rng = np.random.default_rng(21)
+    n_img, lens = 3, [700, 300, 64, 5]
+    all_lens = lens * n_img
+    off = np.concatenate([[0], np.cumsum(all_lens)])
+    bs, ss = [], []
+    for L in all_lens:
+        b, s = synth.make_nms_boxes(rng, L)
+        o = np.argsort(-s, kind="stable")
+        bs.append(b[o]); ss.append(s[o] * rng.uniform(0.5, 1.0))     # levels get different score ranges
+    boxes, scores = np.concatenate(bs), np.concatenate(ss)
+    tb, ts = torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda()
+    to = torch.from_numpy(off.astype(np.int32)).cuda()
+    for post, top_n in ((100, 150), (50, 400)):
+        ki, kc = nms_batched(tb, ts, to, 0.7, post, max(lens))
+        rois, sc, cnt = select_topk(tb, ts, to, ki, kc, n_img, top_n, len(lens) * post)
+        ki_h, kc_h = ki.cpu().numpy(), kc.cpu().numpy()
+        for i in range(n_img):
+            gidx = np.concatenate([off[s] + ki_h[off[s]:off[s] + kc_h[s]] for s in range(i * 4, i * 4 + 4)])
+            order = np.lexsort((gidx, -scores[gidx]))[:top_n]
+            want = gidx[order]
+            n = int(cnt[i])
+            assert n == len(want)
+            got = rois[i * top_n:i * top_n + n].cpu().numpy()
+            assert np.all(got[:, 0] == i)
+            assert np.array_equal(got[:, 1:], boxes[want])
+            assert np.array_equal(sc[i * top_n:i * top_n + n].cpu().numpy(), scores[want])
+            assert np.all(rois[i * top_n + n:(i + 1) * top_n, 1:].cpu().numpy() == 0)
