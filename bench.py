@@ -406,6 +406,28 @@ def run_gpu(args):
             acc[k].append(ev[k][0].elapsed_time(ev[k][1]))
     kms = {k: float(np.median(v)) for k, v in acc.items()}
 
+    # cost of the one-off NCHW -> NHWC re-layout a caller with NCHW-contiguous maps pays per
+    # batch (shared by both poolers and the backward); reported, not part of `value`
+    relayout_ms = None
+    try:
+        lib = _ext.lib()
+        src = [torch.empty((B_IMG, C_FEAT, h, w), device=dev) for (h, w) in shapes[:2]]
+        dst = [torch.empty((B_IMG, C_FEAT, h, w), device=dev, memory_format=torch.channels_last) for (h, w) in shapes[:2]]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for it in range(4):
+            if it == 1:
+                e0.record()
+            for a_, d_ in zip(src, dst):
+                lib.b200_nchw_to_nhwc(_ext.ptr(a_), _ext.ptr(d_), B_IMG, C_FEAT, a_.shape[2], a_.shape[3],
+                                      _ext.stream_ptr(dev))
+        e1.record()
+        torch.cuda.synchronize()
+        frac = sum(h * w for (h, w) in shapes[:2]) / float(sum(h * w for (h, w) in shapes))
+        relayout_ms = e0.elapsed_time(e1) / 3 / frac   # P2+P3 measured, scaled to the whole pyramid
+        del src, dst
+    except Exception:
+        pass
+
     # ---- end to end: host buffers in, host records out, copies inside the timed region ----
     feats_e = [torch.empty(f.shape, dtype=torch.float32, device=dev) for f in feats_h]
     cb_e, cs_e = torch.empty_like(cand_boxes), torch.empty_like(cand_scores)
@@ -480,6 +502,7 @@ def run_gpu(args):
                        "roi_align_mode": "fma (<=1e-5 rel)" if args.fma else "exact (bit-identical to ROIAlign_cpu)",
                        "l2": "inputs (1.46 GB features/GPU) exceed the 126 MB L2; no flush needed",
                        "images_per_sec": world * B_IMG / (ms_step * 1e-3),
+                       "nchw_input_relayout_ms_per_step": relayout_ms,
                        "launch": "eager" if args.no_graph else "CUDA graph replay of the step (all-gather eager)"},
             "clocks": clocks,
             "e2e": {"value": rois_per_step / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,

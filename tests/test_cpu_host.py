@@ -141,3 +141,50 @@ def test_all_gather_records_two_ranks_gloo(tmp_path):
                               stderr=subprocess.STDOUT, text=True) for r in range(2)]
     outs = [p.communicate(timeout=120)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No CUDA extension => ImportError naming the build command; never a silent CPU path."""
+    from cvpr22_cross_modal_pseudo_labeling_b200 import _ext
+    monkeypatch.setattr(_ext, "_lib", None)
+    monkeypatch.setattr(_ext, "LIB_PATH", str(tmp_path / "libb200det.so"))
+    with pytest.raises(ImportError, match="no CPU fallback"):
+        _ext.lib()
+
+
+def test_install_patches_the_reference_when_present():
+    """install() swaps the hot-path objects into an imported maskrcnn_benchmark (only possible
+    where /root/reference exists; the GPU box skips)."""
+    import types
+    if not os.path.isdir("/root/reference/maskrcnn_benchmark"):
+        pytest.skip("reference tree not on this machine")
+    amp = types.ModuleType("apex.amp")
+    amp.float_function = lambda f: f
+    apex = types.ModuleType("apex")
+    apex.amp = amp
+    saved = {k: sys.modules.get(k) for k in ("apex", "apex.amp", "maskrcnn_benchmark._C")}
+    sys.modules["apex"], sys.modules["apex.amp"] = apex, amp
+    sys.path.insert(0, "/root/reference")
+    try:
+        import maskrcnn_benchmark
+        stub = types.ModuleType("maskrcnn_benchmark._C")
+        stub.nms = lambda *a: None
+        sys.modules["maskrcnn_benchmark._C"] = stub
+        maskrcnn_benchmark._C = stub
+        from cvpr22_cross_modal_pseudo_labeling_b200 import layers, modeling
+        from cvpr22_cross_modal_pseudo_labeling_b200.install import install
+        done = install()
+        import maskrcnn_benchmark.modeling.poolers as ref_poolers
+        import maskrcnn_benchmark.structures.boxlist_ops as ref_ops
+        assert ref_poolers.Pooler is modeling.Pooler
+        assert ref_ops._box_nms is layers.nms
+        assert any(d.endswith("rpn.inference.RPNPostProcessor") for d in done)
+    finally:
+        sys.path.remove("/root/reference")
+        for k in [m for m in sys.modules if m.startswith("maskrcnn_benchmark")]:
+            del sys.modules[k]
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
