@@ -114,6 +114,7 @@ embed_match_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tmem_full_bar;
   __shared__ uint32_t tmem_base_slot;
+  __shared__ float stage_tile[4 * 32 * 17];  // epilogue transpose tiles, one per epilogue warp
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row0 = (long long)blockIdx.x * kBM;
@@ -222,19 +223,28 @@ embed_match_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         mx = cmx;
       }
       const float inv = 1.0f / sum;
-      // pass 2: outputs
+      // pass 2: outputs.  A thread holds 16 consecutive columns of ITS row; written directly,
+      // a warp store would touch 32 rows x 4 bytes (32 sectors).  The 32x16 chunk is transposed
+      // through a warp-private shared tile so that half a warp writes 64 contiguous bytes of one
+      // row: 2 rows per store instruction, ~5 sectors instead of 32.
       if (p.probs || p.logits) {
-        for (int c0 = 0; c0 < N; c0 += 16) {
-          tmem_ld16(taddr + c0, v);
-          if (row_ok) {
+        float* tile = stage_tile + (warp - 2) * (32 * 17);
+        const int rsub = lane >> 4, csub = lane & 15;
+        for (int which = 0; which < 2; ++which) {
+          float* outp = which == 0 ? p.logits : p.probs;
+          if (!outp) continue;
+          for (int c0 = 0; c0 < N; c0 += 16) {
+            tmem_ld16(taddr + c0, v);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int c = c0 + i;
-              if (c < N) {
-                if (p.logits) p.logits[row * N + c] = v[i];
-                if (p.probs) p.probs[row * N + c] = __expf(v[i] - mx) * inv;
-              }
+            for (int i = 0; i < 16; ++i) tile[lane * 17 + i] = which == 0 ? v[i] : __expf(v[i] - mx) * inv;
+            __syncwarp();
+            const int c = c0 + csub;
+#pragma unroll 4
+            for (int rr = 0; rr < 32; rr += 2) {
+              const long long orow = row0 + quad * 32 + rr + rsub;
+              if (orow < p.M && c < N) outp[orow * N + c] = tile[(rr + rsub) * 17 + csub];
             }
+            __syncwarp();
           }
         }
       }
