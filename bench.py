@@ -319,7 +319,7 @@ def run_gpu(args):
         pooled, levels = roi_align_forward(feats_d, scales, rois, (7, 7), 2, want_levels=True)
         mark("pool7", 1)
         # 4. head stub (library GEMMs): mean-pool + fc -> bf16 embeddings
-        emb = torch.nn.functional.linear(torch.mv(pooled.view(-1, 49), ones49).view(-1, C_FEAT).to(torch.bfloat16), Wfc_bf)
+        emb = torch.nn.functional.linear(torch.nn.functional.avg_pool2d(pooled, 7).flatten(1).to(torch.bfloat16), Wfc_bf)
         # 5-6. scoring + caption alignment
         mark("match", 0)
         cls = embed_match_softmax(emb, E_d, 0.05, want_probs=True)

@@ -110,6 +110,9 @@ class _NhwcCache(object):
             ref, version, y = e
             if ref() is x and x._version == version:
                 return y
+        # drop copies whose source tensor is gone, so the cache never pins dead feature maps
+        for k in [k for k, (ref, _, _) in self.entries.items() if ref() is None]:
+            del self.entries[k]
         b, c, h, w = x.shape
         src = x.detach()
         y = torch.empty((b, c, h, w), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)

@@ -38,11 +38,16 @@ def all_gather_records(records, counts, sizes=None):
         sz = [torch.zeros_like(n_local) for _ in range(ws)]
         dist.all_gather(sz, n_local)
         sizes = [int(s.item()) for s in sz]
-    if len(set(sizes)) == 1:  # equal shards: no padding, two collectives, no sync
-        out_r = torch.empty((ws * sizes[0],) + tuple(records.shape[1:]), dtype=records.dtype, device=records.device)
-        out_c = torch.empty((ws * sizes[0],), dtype=counts.dtype, device=counts.device)
-        dist.all_gather_into_tensor(out_r, records.contiguous())
-        dist.all_gather_into_tensor(out_c, counts.contiguous())
+    if len(set(sizes)) == 1:
+        # equal shards: records and counts travel in ONE collective (counts ride along as fp32,
+        # exact for any realistic count), no padding, no host sync
+        nrec = records.numel()
+        flat = torch.cat([records.reshape(-1), counts.to(records.dtype)])
+        out = torch.empty((ws * flat.numel(),), dtype=records.dtype, device=records.device)
+        dist.all_gather_into_tensor(out, flat)
+        out = out.view(ws, -1)
+        out_r = out[:, :nrec].reshape((ws * sizes[0],) + tuple(records.shape[1:]))
+        out_c = out[:, nrec:].reshape(-1).to(counts.dtype)
         return out_r, out_c
     n_max = max(sizes)
     pad_r = torch.zeros((n_max,) + tuple(records.shape[1:]), dtype=records.dtype, device=records.device)

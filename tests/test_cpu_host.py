@@ -128,6 +128,11 @@ for i in range(lo, hi):
 allr, allc = all_gather_records(rec, cnt)
 assert allr.shape == (n_img, 4, 8) and allc.tolist() == [i % 4 for i in range(n_img)], (allr.shape, allc)
 assert allr[:, 0, 0].tolist() == list(range(n_img))
+# equal shards with known sizes: the single-collective path
+rec2 = torch.full((3, 4, 8), float(rank)); cnt2 = torch.tensor([rank, rank + 1, rank + 2], dtype=torch.int32)
+r2, c2 = all_gather_records(rec2, cnt2, sizes=[3] * ws)
+assert r2.shape == (3 * ws, 4, 8) and c2.dtype == torch.int32
+assert c2.tolist() == [0, 1, 2, 1, 2, 3] and r2[:, 0, 0].tolist() == [0.0] * 3 + [1.0] * 3
 dist.barrier(); dist.destroy_process_group()
 print("ok", rank)
 '''
