@@ -8,12 +8,13 @@ from tests import synth
 B, n, C = 16, 1000, 256
 res = int(sys.argv[1]) if len(sys.argv) > 1 else 7
 variants = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0]
+exact = (sys.argv[3] != "fast") if len(sys.argv) > 3 else True
 rng = np.random.default_rng(1236)
 g = torch.Generator(device="cuda").manual_seed(1236)
 feats = [torch.randn((B, C, h, w), device="cuda", generator=g).contiguous(memory_format=torch.channels_last) for (h, w) in synth.fpn_shapes()]
 rois = torch.from_numpy(synth.make_rois(rng, n, B)).cuda()
 for v in variants:
-    _ext.debug_set(False, True, v)
+    _ext.debug_set(False, exact, v)
     for _ in range(2):
         _forward(feats, synth.FPN_SCALES, rois, (res, res), 2)
 torch.cuda.synchronize()

@@ -53,7 +53,7 @@ def main():
             out_bytes = R * C * res_ * res_ * 4
             algo = pyr_bytes + out_bytes + R * 20
             for exact in (True, False):
-                for pk in (0, 1):
+                for pk in (0, 1, 2):
                     _ext.debug_set(False, exact, pk)
                     med, best = timeit(lambda: _forward(feats, synth.FPN_SCALES, rois, (res_, res_), 2))
                     key = "fwd_%s_%s_v%d" % (name, "exact" if exact else "fma", pk)
