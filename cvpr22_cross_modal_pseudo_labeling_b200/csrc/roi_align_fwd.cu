@@ -20,12 +20,11 @@
 //
 // kExact=true reproduces the reference's arithmetic bit for bit (separately rounded
 // multiplies and adds in its order); kExact=false lets the 4-tap sum use FMAs.
-#include "roi_geom.cuh"
+#include "roi_align_fwd.cuh"
 
 namespace b200 {
 namespace {
 
-constexpr int kChunk = 64;        // channels per CTA in the staged kernel
 
 template <bool kExact>
 __device__ __forceinline__ float tap4(float w1, float v1, float w2, float v2, float w3, float v3, float w4,
@@ -53,24 +52,6 @@ __device__ __forceinline__ float4 tap4v(float w1, float4 a, float w2, float4 b, 
 
 __device__ __forceinline__ float4 add4(float4 a, float4 b) {
   return make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w));
-}
-
-struct RoiHeader {
-  int batch, level;
-  float x1, y1, x2, y2;
-};
-
-__device__ __forceinline__ RoiHeader load_roi(const float* __restrict__ rois, long long r,
-                                              const LevelTable& lt) {
-  const float* p = rois + r * 5;
-  RoiHeader h;
-  h.batch = (int)p[0];
-  h.x1 = p[1];
-  h.y1 = p[2];
-  h.x2 = p[3];
-  h.y2 = p[4];
-  h.level = lt.n_levels == 1 ? 0 : fpn_level(h.x1, h.y1, h.x2, h.y2, lt.k_min, lt.k_max);
-  return h;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -136,10 +117,6 @@ __device__ void generic_roi(const float* __restrict__ feat, int C, int H, int W,
   }
 }
 
-__device__ __forceinline__ void zero_fill(float* __restrict__ p, int n, int tid, int nthreads) {
-  for (int i = tid; i < n; i += nthreads) p[i] = 0.f;
-}
-
 // grid.x = n_rois * ceil(C / c_per_cta)
 template <bool kExact, int kLayout>
 __global__ void __launch_bounds__(256)
@@ -161,31 +138,6 @@ roi_align_fwd_generic(const LevelTable lt, int C, const float* __restrict__ rois
   const RoiGeom g = roi_geometry(h.x1, h.y1, h.x2, h.y2, lt.scale[h.level], PH, PW, sampling_ratio);
   generic_roi<kExact, kLayout>(lt.data[h.level], C, lt.H[h.level], lt.W[h.level], h.batch, g, PH, PW, c_begin,
                                c_count, out_roi, threadIdx.x, blockDim.x);
-}
-
-// ---------------------------------------------------------------------------------------
-// Shared-memory output tile [64 channels x NB bins] of the marching kernels.  A warp stores one
-// float per lane with lanes spread over channel quads, i.e. at a stride of 4*NB floats: for
-// NB = 196 (14x14) that is 16 banks apart, an 8-way conflict.  When NB % 4 == 0 the row of
-// channel c is therefore shifted by 4 * (c >> 3) floats (monotonic, so rows never overlap;
-// keeps rows 16-byte aligned for the vectorised copy-out; leaves at most a 2-way conflict).
-// ---------------------------------------------------------------------------------------
-__device__ __forceinline__ int tile_row(int c, int NB, bool swz) { return c * NB + (swz ? 4 * (c >> 3) : 0); }
-constexpr int kTilePadFloats = 32;
-
-__device__ __forceinline__ void tile_copy_out(const float* out_s, float* __restrict__ dst_f, int NB, bool swz,
-                                              int tid, int nthreads) {
-  float4* dst = reinterpret_cast<float4*>(dst_f);
-  const float4* src = reinterpret_cast<const float4*>(out_s);
-  if (!swz) {
-    for (int i = tid; i < kChunk * NB / 4; i += nthreads) __stcs(dst + i, src[i]);
-  } else {
-    const int rowv = NB >> 2;  // float4 per channel row
-    for (int i = tid; i < kChunk * rowv; i += nthreads) {
-      const int c = i / rowv;
-      __stcs(dst + i, src[i + (c >> 3)]);
-    }
-  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -325,212 +277,6 @@ roi_align_fwd_march(const LevelTable lt, int C, const float* __restrict__ rois, 
   tile_copy_out(out_s, out_roi + (size_t)c_begin * NB, NB, swz, tid, kThreads);
 }
 
-// ---------------------------------------------------------------------------------------
-// Separable marching kernel (NHWC, sampling_ratio == 2) -- the "fast math" forward.
-// Bilinear interpolation factorises: a bin's sum is
-//     sum_ix [ hx * T(x_lo) + lx * T(x_hi) ],   T(x) = sum_k w_k * f(row_k, x)
-// where row_k / w_k are the (up to four, duplicates merged) tap rows of the output row's two
-// y-samples.  A thread (4 channels, one output row) reduces every feature column it needs to
-// ONE float4 as soon as the column's tap rows arrive and never keeps raw taps, which frees
-// the registers to keep kDepth columns in flight per thread.
-// What bounds this kernel is the L1 data pipe (ncu: l1tex__data_pipe_lsu_wavefronts), one
-// wavefront per 128-byte line a request touches -- so 8 lanes of a warp cover one 128 B run of a
-// pixel (8 channel quads), duplicate tap rows are not loaded twice, and the tile stores are
-// bank-conflict free.
-// The result differs from the reference's summation order by fp32 reassociation only
-// (<= 1e-5 relative, tests/test_gpu_roi_align.py); the exact kernel stays available.
-// ---------------------------------------------------------------------------------------
-struct XSample {
-  int jhi;     // index (in the CTA's column list) of the sample's right tap column
-  float l, h;  // weights of the right / left tap (left == right column: l = l + h, h = 0)
-  int pad;
-};
-constexpr int kMaxCols = 2 * kMaxAxisSamples;
-
-__device__ __forceinline__ float4 ldg4b(const char* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-
-__device__ __forceinline__ float4 fma4(float w, float4 v, float4 a) {
-  return make_float4(fmaf(w, v.x, a.x), fmaf(w, v.y, a.y), fmaf(w, v.z, a.z), fmaf(w, v.w, a.w));
-}
-
-template <int kThreads, int kMinBlocks, int kDepth>
-__global__ void __launch_bounds__(kThreads, kMinBlocks)
-roi_align_fwd_sep(const LevelTable lt, int C, const float* __restrict__ rois, int PH, int PW,
-                  float* __restrict__ out, int32_t* __restrict__ out_levels) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int NB = PH * PW;
-  const bool swz = (NB & 3) == 0;
-  float* out_s = reinterpret_cast<float*>(smem_raw);
-  AxisEntry* ytab = reinterpret_cast<AxisEntry*>(smem_raw + sizeof(float) * (kChunk * NB + kTilePadFloats));
-  XSample* xs = reinterpret_cast<XSample*>(ytab + kMaxAxisSamples);
-  int* colofs = reinterpret_cast<int*>(xs + kMaxAxisSamples + 1);  // byte offsets
-  __shared__ int ncols_s;
-
-  const int tid = threadIdx.x;
-  const int n_cchunks = C / kChunk;
-  const long long r = blockIdx.x / n_cchunks;
-  const int ck = blockIdx.x % n_cchunks;
-  const int c_begin = ck * kChunk;
-  const RoiHeader h = load_roi(rois, r, lt);
-  float* out_roi = out + (size_t)r * C * NB;
-  if (ck == 0 && tid == 0 && out_levels) out_levels[r] = h.level;
-  if (h.level < 0) {
-    zero_fill(out_roi + (size_t)c_begin * NB, kChunk * NB, tid, kThreads);
-    return;
-  }
-  const int H = lt.H[h.level], W = lt.W[h.level];
-  const RoiGeom g = roi_geometry(h.x1, h.y1, h.x2, h.y2, lt.scale[h.level], PH, PW, 2);
-  const int warp = tid >> 5, lane = tid & 31;
-  const int ns = 2 * PW;
-
-  // warp 0: row table.  warp 1: sample table + the list of distinct columns in the order the
-  // march needs them (a sample either reuses the previous columns, shifts by one, or starts
-  // a new pair).
-  if (warp == 0) {
-    bool ok = false;
-    AxisTap t;
-    t.lo = t.hi = 0;
-    t.l = t.h = 0.f;
-    if (lane < 2 * PH) t = axis_sample(g.start_h, lane >> 1, g.bin_h, lane & 1, 2, H, ok);
-    ok = ok && lane < 2 * PH;
-    AxisEntry e;
-    e.lo = ok ? t.lo * W * C : 0;
-    e.hi = ok ? t.hi * W * C : 0;
-    e.l = ok ? t.l : 0.f;
-    e.h = ok ? t.h : 0.f;
-    if (lane < 2 * PH) ytab[lane] = e;
-  } else if (warp == 1) {
-    bool ok = false;
-    AxisTap t;
-    t.lo = t.hi = 0;
-    t.l = t.h = 0.f;
-    if (lane < ns) t = axis_sample(g.start_w, lane >> 1, g.bin_w, lane & 1, 2, W, ok);
-    ok = ok && lane < ns;
-    const int lo = ok ? t.lo * C : 0, hi = ok ? t.hi * C : 0;
-    const int plo = __shfl_up_sync(0xffffffffu, lo, 1), phi = __shfl_up_sync(0xffffffffu, hi, 1);
-    int act = kActLoad2;
-    if (lane > 0) {
-      if (lo == plo && hi == phi) act = kActReuse;
-      else if (lo == phi) act = kActShift;
-    }
-    int nnew = act == kActReuse ? 0 : (act == kActShift ? 1 : (lo == hi ? 1 : 2));
-    if (lane >= ns) nnew = 0;
-    int scan = nnew;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, scan, d);
-      if (lane >= d) scan += v;
-    }
-    if (lane < ns) {
-      XSample e;
-      e.jhi = scan - 1;
-      const float wl = ok ? t.l : 0.f, wh = ok ? t.h : 0.f;
-      e.l = lo == hi ? wl + wh : wl;
-      e.h = lo == hi ? 0.f : wh;
-      e.pad = 0;
-      xs[lane] = e;
-      if (nnew >= 1) colofs[scan - 1] = hi * 4;
-      if (nnew == 2) colofs[scan - 2] = lo * 4;
-    }
-    if (lane == 31) {
-      ncols_s = scan;
-      xs[ns].jhi = -1;  // sentinel: ends the consume loop after the last sample
-    }
-  }
-  __syncthreads();
-
-  const int ncols = ncols_s;
-  const float* feat = lt.data[h.level] + (size_t)h.batch * H * W * C + c_begin;
-  constexpr int kWarps = kThreads / 32;
-  constexpr int kGroups = kChunk / 4;
-  constexpr int kLQ = kWarps <= 4 ? 8 : 16;  // channel quads side by side in a warp (128 / 256 B runs)
-  constexpr int kQGroups = kGroups / kLQ;
-  {
-    const int q = (warp % kQGroups) * kLQ + (lane % kLQ);
-    const int ph = lane / kLQ + (32 / kLQ) * (warp / kQGroups);
-    if (ph < PH) {
-      const AxisEntry ya = ytab[2 * ph], yb = ytab[2 * ph + 1];
-      int row[4] = {ya.lo, ya.hi, yb.lo, yb.hi};
-      float w[4] = {ya.h, ya.l, yb.h, yb.l};
-      bool use[4] = {true, true, true, true};
-#pragma unroll
-      for (int k = 1; k < 4; ++k) {
-#pragma unroll
-        for (int j = 0; j < k; ++j) {
-          if (use[k] && row[k] == row[j]) {  // the earliest occurrence of a row is never merged away
-            w[j] += w[k];
-            w[k] = 0.f;
-            use[k] = false;
-          }
-        }
-      }
-      const char* rp[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) rp[k] = reinterpret_cast<const char*>(feat + (unsigned)(row[k] + 4 * q));
-      float4 raw[kDepth][4];
-#pragma unroll
-      for (int d = 0; d < kDepth; ++d) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) raw[d][k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (d < ncols) {
-          const unsigned co = (unsigned)colofs[d];
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (use[k]) raw[d][k] = ldg4b(rp[k] + co);
-        }
-      }
-      float4 t[2];
-      t[0] = t[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      float* o0 = out_s + tile_row(4 * q, NB, swz) + ph * PW;  // the quad's 4 rows share one shift
-      int s = 0;
-      XSample e = xs[0];
-      constexpr int kUnroll = (kDepth % 2 == 0) ? kDepth : 2 * kDepth;
-      for (int j0 = 0; j0 < ncols; j0 += kUnroll) {
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-          const int j = j0 + u;
-          if (j < ncols) {
-            float4 (&rw)[4] = raw[u % kDepth];
-            float4 tv = make_float4(w[0] * rw[0].x, w[0] * rw[0].y, w[0] * rw[0].z, w[0] * rw[0].w);
-            tv = fma4(w[1], rw[1], tv);
-            tv = fma4(w[2], rw[2], tv);
-            tv = fma4(w[3], rw[3], tv);
-            t[u & 1] = tv;
-            if (j + kDepth < ncols) {
-              const unsigned co = (unsigned)colofs[j + kDepth];
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (use[k]) rw[k] = ldg4b(rp[k] + co);
-            }
-            while (e.jhi == j) {
-              acc = fma4(e.h, t[(u & 1) ^ 1], acc);
-              acc = fma4(e.l, t[u & 1], acc);
-              if (s & 1) {
-                float* o = o0 + (s >> 1);
-                o[0] = acc.x * 0.25f;
-                o[NB] = acc.y * 0.25f;
-                o[2 * NB] = acc.z * 0.25f;
-                o[3 * NB] = acc.w * 0.25f;
-                acc = make_float4(0.f, 0.f, 0.f, 0.f);
-              }
-              ++s;
-              e = xs[s];  // xs[ns] is a sentinel (jhi = -1)
-            }
-          }
-        }
-      }
-    }
-  }
-  __syncthreads();
-  tile_copy_out(out_s, out_roi + (size_t)c_begin * NB, NB, swz, tid, kThreads);
-}
-
-size_t sep_smem_bytes(int NB) {
-  return sizeof(float) * (kChunk * NB + kTilePadFloats) + kMaxAxisSamples * sizeof(AxisEntry) +
-         (kMaxAxisSamples + 1) * sizeof(XSample) + kMaxCols * sizeof(int);
-}
-
 size_t march_smem_bytes(int NB) {
   return sizeof(float) * (kChunk * NB + kTilePadFloats) + 2 * kMaxAxisSamples * sizeof(AxisEntry);
 }
@@ -553,20 +299,6 @@ int launch_march(const LevelTable& lt, int C, const float* rois, int64_t n_rois,
   return B200_OK;
 }
 
-template <int kThreads, int kMinBlocks, int kDepth>
-int launch_sep(const LevelTable& lt, int C, const float* rois, int64_t n_rois, int PH, int PW, float* out,
-               int32_t* out_levels, cudaStream_t st) {
-  const size_t smem = sep_smem_bytes(PH * PW);
-  auto kern = roi_align_fwd_sep<kThreads, kMinBlocks, kDepth>;
-  static SmemHighWater hw;
-  int rc = ensure_dynamic_smem(kern, smem, &hw, "roi_align: smem attribute");
-  if (rc != B200_OK) return rc;
-  const int64_t grid = n_rois * (C / kChunk);
-  kern<<<(unsigned)grid, kThreads, smem, st>>>(lt, C, rois, PH, PW, out, out_levels);
-  B200_CHECK_LAUNCH("roi_align_fwd_sep");
-  return B200_OK;
-}
-
 template <bool kExact>
 int launch_forward(const LevelTable& lt, int layout, int C, const float* rois, int64_t n_rois, int PH, int PW,
                    int sr, float* out, int32_t* out_levels, cudaStream_t st) {
@@ -574,16 +306,7 @@ int launch_forward(const LevelTable& lt, int layout, int C, const float* rois, i
   const bool march_ok = !g_force_generic && layout == B200_LAYOUT_NHWC && sr == 2 && PH <= 16 && PW <= 16 &&
                         C % kChunk == 0 && (NB * kChunk) % 4 == 0;
   B200_REQUIRE(n_rois * ((C + 15) / 16) < (int64_t)1 << 31, "roi_align: too many RoIs for one launch");
-  if (march_ok && !kExact) {
-    if (PH * (kChunk / 4) <= 128) {
-      if (g_variant == 1) return launch_sep<128, 6, 2>(lt, C, rois, n_rois, PH, PW, out, out_levels, st);
-      if (g_variant == 2) return launch_sep<128, 6, 3>(lt, C, rois, n_rois, PH, PW, out, out_levels, st);
-      return launch_sep<128, 8, 2>(lt, C, rois, n_rois, PH, PW, out, out_levels, st);
-    }
-    if (g_variant == 1) return launch_sep<256, 3, 2>(lt, C, rois, n_rois, PH, PW, out, out_levels, st);
-    if (g_variant == 2) return launch_sep<256, 3, 3>(lt, C, rois, n_rois, PH, PW, out, out_levels, st);
-    return launch_sep<256, 4, 2>(lt, C, rois, n_rois, PH, PW, out, out_levels, st);
-  }
+  if (march_ok && !kExact) return launch_forward_sep(lt, C, rois, n_rois, PH, PW, out, out_levels, g_variant, st);
   if (march_ok) {
     // g_variant (tuning hook): CTAs/SM = 6 (default) / 5 / 4 for 128 threads, 3 / 3 / 2 for 256.
     // (2 channels per lane with twice the warps was measured 35-55 % slower: V stays 4.)
