@@ -260,7 +260,7 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _ext.lib()
-    _ext.debug_set(False, not args.fma, 0)
+    _ext.debug_set(False, True, 0)
 
     seed = 1236 + 1000 * rank
     rng = np.random.default_rng(seed)
@@ -316,7 +316,7 @@ def run_gpu(args):
         rois, _, _ = select_topk(cand_boxes, cand_scores, seg_off, keep_idx, keep_cnt, B_IMG, R_IMG, 5 * 1000)
         # 3. box pooler
         mark("pool7", 0)
-        pooled, levels = roi_align_forward(feats_d, scales, rois, (7, 7), 2, want_levels=True)
+        pooled, levels = roi_align_forward(feats_d, scales, rois, (7, 7), 2, want_levels=True, math=args.math)
         mark("pool7", 1)
         # 4. head stub (library GEMMs): mean-pool + fc -> bf16 embeddings
         emb = torch.nn.functional.linear(torch.nn.functional.avg_pool2d(pooled, 7).flatten(1).to(torch.bfloat16), Wfc_bf)
@@ -330,7 +330,7 @@ def run_gpu(args):
         sel = rois[word_base + idx]
         # 7. mask pooler on the aligned boxes
         mark("pool14", 0)
-        mask_feat, _ = roi_align_forward(feats_d, scales, sel, (14, 14), 2)
+        mask_feat, _ = roi_align_forward(feats_d, scales, sel, (14, 14), 2, math=args.math)
         mark("pool14", 1)
         # 8. records (img, word slot, box, score, region)
         rec = torch.zeros((B_IMG, w_max, 8), dtype=torch.float32, device=dev)
@@ -405,6 +405,17 @@ def run_gpu(args):
         for k in ev:
             acc[k].append(ev[k][0].elapsed_time(ev[k][1]))
     kms = {k: float(np.median(v)) for k, v in acc.items()}
+    # the box pooler in the other arithmetic mode, same RoIs, for the record
+    other = "exact" if args.math == "fast" else "fast"
+    ts = []
+    for _ in range(5):
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        roi_align_forward(feats, scales, state["rois"], (7, 7), 2, math=other)
+        a1.record()
+        a1.synchronize()
+        ts.append(a0.elapsed_time(a1))
+    kms["pool7_%s_math" % other] = float(np.median(ts[1:]))
 
     # cost of the one-off NCHW -> NHWC re-layout a caller with NCHW-contiguous maps pays per
     # batch (shared by both poolers and the backward); reported, not part of `value`
@@ -499,7 +510,8 @@ def run_gpu(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "images_per_gpu": B_IMG, "rois_per_image": R_IMG,
                        "feature_layout": "channels_last (NHWC memory, logical [B,C,H,W])",
-                       "roi_align_mode": "fma (<=1e-5 rel)" if args.fma else "exact (bit-identical to ROIAlign_cpu)",
+                       "roi_align_math": ("fast: separable FMA evaluation, <= 1e-5 rel of ROIAlign_cpu (b200_roi_align_forward_fast)"
+                                          if args.math == "fast" else "exact: bit-identical to ROIAlign_cpu (b200_roi_align_forward)"),
                        "l2": "inputs (1.46 GB features/GPU) exceed the 126 MB L2; no flush needed",
                        "images_per_sec": world * B_IMG / (ms_step * 1e-3),
                        "nchw_input_relayout_ms_per_step": relayout_ms,
@@ -509,7 +521,7 @@ def run_gpu(args):
                     "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(rec_h.numel() * 4 + cnt_h.numel() * 4) // world},
             "gpu_launches": args.steps * 7,  # nms, select, pool7, softmax match, colmax match, decode, pool14
             "kernel_ms": kms,
-            "roofline": {"kernel": "roi_align_fwd_march (box pooler 7x7)", "bound": "hbm", "achieved": achieved,
+            "roofline": {"kernel": "%s (box pooler 7x7)" % ("roi_align_fwd_sep" if args.math == "fast" else "roi_align_fwd_march"), "bound": "hbm", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                          "algorithmic_bytes": int(algo), "f_touched_bytes": int(ft), "traffic": traffic},
@@ -540,7 +552,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--fma", action="store_true", help="RoIAlign FMA mode (<=1e-5 rel) instead of bit-exact")
+    ap.add_argument("--math", default="fast", choices=["fast", "exact"],
+                    help="RoIAlign forward arithmetic: fast = separable FMA evaluation (<= 1e-5 rel, the tolerance "
+                         "BASELINE.json states); exact = the reference's operation order, bit-identical")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()

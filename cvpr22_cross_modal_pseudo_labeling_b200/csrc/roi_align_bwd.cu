@@ -9,7 +9,7 @@
 //         (red.global.add.v4.f32) instead of four scalar atomics.
 //   NCHW: a thread owns (channel, bin) with scalar reductions, bins fastest so that the
 //         reads of grad_out are coalesced.
-#include "roi_geom.cuh"
+#include "roi_align_fwd.cuh"
 
 namespace b200 {
 namespace {
@@ -93,69 +93,62 @@ roi_align_bwd_generic(const LevelGradTable lt, int C, const float* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------
-// Marching backward (NHWC, sampling_ratio == 2, PH,PW <= 16, C % 64 == 0): mirror of
-// roi_align_fwd_march.  One CTA per (RoI, 64-channel chunk) stages its [64 x NB] tile of
-// grad_out in shared memory (one coalesced read).  A thread owns (4 channels, one output row)
-// and marches along x with two register columns of ACCUMULATORS (4 tap rows x float4): every
-// sample adds its four (top * w) / count terms into them, and a column is written out with
-// four red.global.add.v4.f32 only when the march leaves it -- 2-3x fewer reductions than one
-// per tap, each 128 bits wide.
+// Marching kernel (NHWC, sampling_ratio == 2, PH,PW <= 16, C % 64 == 0): the transpose of the
+// separable forward (roi_align_fwd_sep.cu).  A thread owns (4 channels, one output row) and
+// walks the row's x-samples left to right.  Each bin's gradient (x 1/count) is spread over the
+// two tap COLUMNS of each sample into two float4 column accumulators; when the march leaves a
+// column its accumulator is scaled by the (up to four, duplicates merged) tap-row weights and
+// written with one 128-bit red.global.add.v4.f32 per row: ~3.3 reductions per column instead
+// of 16 per bin, 8 lanes side by side covering one 128-byte line.  One CTA per RoI walks all
+// (up to 4) 64-channel chunks so the geometry and tables are built once per RoI.
+// The addends are algebraically the reference's (top * w_y * w_x) / count
+// (ROIAlign_cuda.cu:161-172, :239-242) summed per (row, column) before they reach memory;
+// fp32 rounding differs from the per-tap kernel by reassociation only, and the order of the
+// atomic additions is free in the reference too.
 // ---------------------------------------------------------------------------------------
 constexpr int kChunkB = 64;
 
-struct Acc4 {
-  float v[4];
-};
-
-// rows[1] (upper sample's high tap row) and rows[2] (lower sample's low tap row) coincide
-// whenever both samples of the bin fall in adjacent cells: one reduction then carries both.
-__device__ __forceinline__ void flush_col(float* __restrict__ gfeat, const int (&rows)[4], int col, Acc4 (&g)[4]) {
-  const bool dup = rows[1] == rows[2];
-  if (dup) {
-#pragma unroll
-    for (int c = 0; c < 4; ++c) g[1].v[c] += g[2].v[c];
-  }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    if (!(k == 2 && dup))
-      red_add_v4(gfeat + (unsigned)(rows[k] + col), g[k].v[0], g[k].v[1], g[k].v[2], g[k].v[3]);
-    g[k].v[0] = g[k].v[1] = g[k].v[2] = g[k].v[3] = 0.f;
-  }
+__device__ __forceinline__ float4 lds128b(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32b(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float ldsf(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
 }
 
-// add one sample column's contributions: left taps into Lg, right taps into Rg
-__device__ __forceinline__ void scatter_pair(Acc4 (&Lg)[4], Acc4 (&Rg)[4], const AxisEntry& ya, const AxisEntry& yb,
-                                             const AxisEntry& xt, const float (&top)[4]) {
-  const float w[8] = {__fmul_rn(ya.h, xt.h), __fmul_rn(ya.h, xt.l), __fmul_rn(ya.l, xt.h), __fmul_rn(ya.l, xt.l),
-                      __fmul_rn(yb.h, xt.h), __fmul_rn(yb.h, xt.l), __fmul_rn(yb.l, xt.h), __fmul_rn(yb.l, xt.l)};
+__device__ __forceinline__ void red_col(char* const (&rp)[4], const bool (&use)[4], const float (&w)[4], uint32_t co,
+                                        const float4& t) {
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    // (top * w) / count with count = 4: the division is exact, as a multiply by 0.25
-    Lg[0].v[c] += __fmul_rn(__fmul_rn(top[c], w[0]), 0.25f);
-    Rg[0].v[c] += __fmul_rn(__fmul_rn(top[c], w[1]), 0.25f);
-    Lg[1].v[c] += __fmul_rn(__fmul_rn(top[c], w[2]), 0.25f);
-    Rg[1].v[c] += __fmul_rn(__fmul_rn(top[c], w[3]), 0.25f);
-    Lg[2].v[c] += __fmul_rn(__fmul_rn(top[c], w[4]), 0.25f);
-    Rg[2].v[c] += __fmul_rn(__fmul_rn(top[c], w[5]), 0.25f);
-    Lg[3].v[c] += __fmul_rn(__fmul_rn(top[c], w[6]), 0.25f);
-    Rg[3].v[c] += __fmul_rn(__fmul_rn(top[c], w[7]), 0.25f);
-  }
+  for (int k = 0; k < 4; ++k)
+    if (use[k])
+      red_add_v4(reinterpret_cast<float*>(rp[k] + co), w[k] * t.x, w[k] * t.y, w[k] * t.z, w[k] * t.w);
 }
 
 template <int kThreads, int kMinBlocks>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 roi_align_bwd_march(const LevelGradTable lt, int C, const float* __restrict__ rois, int PH, int PW,
-                    const float* __restrict__ grad_out) {
+                    int chunks_per_cta, const float* __restrict__ grad_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int NB = PH * PW;
+  const bool swz = (NB & 3) == 0;
   float* g_s = reinterpret_cast<float*>(smem_raw);
-  AxisEntry* ytab = reinterpret_cast<AxisEntry*>(smem_raw + sizeof(float) * kChunkB * NB);
-  AxisEntry* xtab = ytab + kMaxAxisSamples;
+  AxisEntry* ytab = reinterpret_cast<AxisEntry*>(smem_raw + sizeof(float) * (kChunkB * NB + kTilePadFloats));
+  XSample* xs = reinterpret_cast<XSample*>(ytab + kMaxAxisSamples);
+  int* colofs = reinterpret_cast<int*>(xs + kMaxAxisSamples + 1);
+  __shared__ int ncols_s;
 
   const int tid = threadIdx.x;
-  const int n_cchunks = C / kChunkB;
-  const long long r = blockIdx.x / n_cchunks;
-  const int c_begin = (blockIdx.x % n_cchunks) * kChunkB;
+  const int groups = C / (kChunkB * chunks_per_cta);
+  const long long r = blockIdx.x / groups;
+  const int c0 = (blockIdx.x % groups) * chunks_per_cta * kChunkB;
   const float* p = rois + r * 5;
   const int batch = (int)p[0];
   const float x1 = p[1], y1 = p[2], x2 = p[3], y2 = p[4];
@@ -163,69 +156,78 @@ roi_align_bwd_march(const LevelGradTable lt, int C, const float* __restrict__ ro
   if (level < 0) return;
   const int H = lt.H[level], W = lt.W[level];
   const RoiGeom g = roi_geometry(x1, y1, x2, y2, lt.scale[level], PH, PW, 2);
-
-  // this CTA's contiguous [64 x NB] block of grad_out
-  const float4* src = reinterpret_cast<const float4*>(grad_out + ((size_t)r * C + c_begin) * NB);
-  float4* dst = reinterpret_cast<float4*>(g_s);
-  for (int i = tid; i < kChunkB * NB / 4; i += kThreads) dst[i] = __ldcs(src + i);
   const int warp = tid >> 5, lane = tid & 31;
-  build_axis_tables(g, PH, PW, H, W, C, warp, lane, ytab, xtab);
+  build_sep_tables(g, PH, PW, H, W, C, warp, lane, ytab, xs, colofs, &ncols_s);
   __syncthreads();
 
+  const int ncols = ncols_s;
   constexpr int kGroups = kChunkB / 4;
   constexpr int kWarps = kThreads / 32;
-  constexpr int kLQ = kGroups / kWarps >= 4 ? 4 : 16;
+  constexpr int kLQ = kWarps <= 4 ? 8 : 16;  // channel quads side by side: 128 / 256 B runs per reduction
   constexpr int kQGroups = kGroups / kLQ;
   const int q = (warp % kQGroups) * kLQ + (lane % kLQ);
   const int ph = lane / kLQ + (32 / kLQ) * (warp / kQGroups);
-  if (ph >= PH) return;
-  float* gfeat = lt.data[level] + (size_t)batch * H * W * C + c_begin;
-  const AxisEntry ya = ytab[2 * ph], yb = ytab[2 * ph + 1];
-  const int rows[4] = {ya.lo + 4 * q, ya.hi + 4 * q, yb.lo + 4 * q, yb.hi + 4 * q};
-  Acc4 A[4], B[4];
+  const bool active = ph < PH;
+  int row[4] = {0, 0, 0, 0};
+  float w[4] = {0.f, 0.f, 0.f, 0.f};
+  bool use[4] = {false, false, false, false};
+  if (active) merge_tap_rows(ytab[2 * ph], ytab[2 * ph + 1], row, w, use);
+  float* img = lt.data[level] + (size_t)batch * H * W * C + 4 * q;
+  const uint32_t xs_a = smem_u32(xs), co_a = smem_u32(colofs);
+  const uint32_t g_a = smem_u32(g_s) + 4u * (uint32_t)(tile_row(4 * q, NB, swz) + ph * PW);
+  const uint32_t nb4 = 4u * (uint32_t)NB;
+
+  for (int cc = 0; cc < chunks_per_cta; ++cc) {
+    const int c_begin = c0 + cc * kChunkB;
+    if (cc > 0) __syncthreads();  // everyone is done reading the previous chunk's tile
+    tile_copy_in(g_s, grad_out + ((size_t)r * C + c_begin) * NB, NB, swz, tid, kThreads);
+    __syncthreads();
+    if (active) {
+      char* rp[4];
 #pragma unroll
-  for (int k = 0; k < 4; ++k)
+      for (int k = 0; k < 4; ++k) {
+        rp[k] = reinterpret_cast<char*>(img + c_begin + (unsigned)row[k]);
+        asm volatile("" : "+l"(rp[k]));  // keep the row pointers in registers (see roi_align_fwd_sep.cu)
+      }
+      float4 t[2];
+      t[0] = t[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 top = make_float4(0.f, 0.f, 0.f, 0.f);
+      int s = 0;
+      float4 e = lds128b(xs_a);  // (jhi, l, h, -)
+      for (int j0 = 0; j0 < ncols; j0 += 2) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) A[k].v[c] = B[k].v[c] = 0.f;
-  int a_is_left = 1, col_l = -1, col_r = -1;  // element offsets of the columns held (-1: empty)
-  const float* gt = g_s + (size_t)(4 * q) * NB + ph * PW;
-  for (int pw = 0; pw < PW; ++pw) {
-    const float top[4] = {gt[pw], gt[NB + pw], gt[2 * NB + pw], gt[3 * NB + pw]};
-#pragma unroll
-    for (int ix = 0; ix < 2; ++ix) {
-      const AxisEntry xt = xtab[2 * pw + ix];
-      const int act = xt.lo & 3, xlo = xt.lo & ~3;
-      if (act == kActShift) {
-        // the left column is finished: write it out, the right one becomes the left
-        if (a_is_left) flush_col(gfeat, rows, col_l, A);
-        else flush_col(gfeat, rows, col_l, B);
-        a_is_left ^= 1;
-        col_l = col_r;
-        col_r = xt.hi;
-      } else if (act == kActLoad2) {
-        if (col_l >= 0) {
-          if (a_is_left) {
-            flush_col(gfeat, rows, col_l, A);
-            flush_col(gfeat, rows, col_r, B);
-          } else {
-            flush_col(gfeat, rows, col_l, B);
-            flush_col(gfeat, rows, col_r, A);
+        for (int u = 0; u < 2; ++u) {
+          const int j = j0 + u;
+          if (j < ncols) {
+            // samples whose right tap column is j: they add to columns j-1 (t[u^1]) and j (t[u])
+            while (__float_as_int(e.x) == j) {
+              if (!(s & 1)) {
+                const uint32_t ga = g_a + 4u * (uint32_t)(s >> 1);
+                top.x = 0.25f * ldsf(ga);  // 1 / count, count = 4
+                top.y = 0.25f * ldsf(ga + nb4);
+                top.z = 0.25f * ldsf(ga + 2u * nb4);
+                top.w = 0.25f * ldsf(ga + 3u * nb4);
+              }
+              t[u ^ 1].x = fmaf(e.z, top.x, t[u ^ 1].x);
+              t[u ^ 1].y = fmaf(e.z, top.y, t[u ^ 1].y);
+              t[u ^ 1].z = fmaf(e.z, top.z, t[u ^ 1].z);
+              t[u ^ 1].w = fmaf(e.z, top.w, t[u ^ 1].w);
+              t[u].x = fmaf(e.y, top.x, t[u].x);
+              t[u].y = fmaf(e.y, top.y, t[u].y);
+              t[u].z = fmaf(e.y, top.z, t[u].z);
+              t[u].w = fmaf(e.y, top.w, t[u].w);
+              ++s;
+              e = lds128b(xs_a + 16u * (uint32_t)s);
+            }
+            // column j-1 is complete: nothing right of column j's samples touches it
+            if (j > 0) {
+              red_col(rp, use, w, lds32b(co_a + 4u * (uint32_t)(j - 1)), t[u ^ 1]);
+              t[u ^ 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
           }
         }
-        col_l = xlo;
-        col_r = xt.hi;
       }
-      if (a_is_left) scatter_pair(A, B, ya, yb, xt, top);
-      else scatter_pair(B, A, ya, yb, xt, top);
-    }
-  }
-  if (col_l >= 0) {
-    if (a_is_left) {
-      flush_col(gfeat, rows, col_l, A);
-      flush_col(gfeat, rows, col_r, B);
-    } else {
-      flush_col(gfeat, rows, col_l, B);
-      flush_col(gfeat, rows, col_r, A);
+      red_col(rp, use, w, lds32b(co_a + 4u * (uint32_t)(ncols - 1)), t[(ncols - 1) & 1]);
     }
   }
 }
@@ -266,21 +268,25 @@ extern "C" int b200_roi_align_backward(const b200_level_grad* levels, int n_leve
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!g_bwd_force_generic && layout == B200_LAYOUT_NHWC && sampling_ratio == 2 && pooled_h <= 16 && pooled_w <= 16 &&
       channels % kChunkB == 0 && aligned16(grad_out)) {
-    const int64_t grid = n_rois * (channels / kChunkB);
+    const int n_chunks = channels / kChunkB;
+    int cpc = n_chunks % 4 == 0 ? 4 : (n_chunks % 2 == 0 ? 2 : 1);
+    if (n_rois < 2048) cpc = 1;  // few RoIs: keep the grid wide
+    const int64_t grid = n_rois * (n_chunks / cpc);
     B200_REQUIRE(grid < (int64_t)1 << 31, "roi_align_bwd: too many RoIs for one launch");
-    const size_t smem = sizeof(float) * kChunkB * NB + 2 * kMaxAxisSamples * sizeof(AxisEntry);
+    const size_t smem = sizeof(float) * (kChunkB * NB + kTilePadFloats) + kMaxAxisSamples * sizeof(AxisEntry) +
+                        (kMaxAxisSamples + 1) * sizeof(XSample) + kMaxCols * sizeof(int);
     if (pooled_h <= 8) {
-      auto kern = roi_align_bwd_march<128, 5>;
+      auto kern = roi_align_bwd_march<128, 8>;
       static SmemHighWater hw;
       int rc = ensure_dynamic_smem(kern, smem, &hw, "roi_align_bwd: smem attribute");
       if (rc != B200_OK) return rc;
-      kern<<<(unsigned)grid, 128, smem, st>>>(lt, channels, rois, pooled_h, pooled_w, grad_out);
+      kern<<<(unsigned)grid, 128, smem, st>>>(lt, channels, rois, pooled_h, pooled_w, cpc, grad_out);
     } else {
-      auto kern = roi_align_bwd_march<256, 3>;
+      auto kern = roi_align_bwd_march<256, 4>;
       static SmemHighWater hw;
       int rc = ensure_dynamic_smem(kern, smem, &hw, "roi_align_bwd: smem attribute");
       if (rc != B200_OK) return rc;
-      kern<<<(unsigned)grid, 256, smem, st>>>(lt, channels, rois, pooled_h, pooled_w, grad_out);
+      kern<<<(unsigned)grid, 256, smem, st>>>(lt, channels, rois, pooled_h, pooled_w, cpc, grad_out);
     }
     B200_CHECK_LAUNCH("roi_align_bwd_march");
     return B200_OK;

@@ -369,11 +369,11 @@ extern "C" void b200_debug_set(int force_generic, int exact, int variant) {
   b200::g_variant = variant;
 }
 
-extern "C" int b200_roi_align_forward(const b200_level* levels, int n_levels, int layout, int batch,
-                                      int channels, const float* rois, int64_t n_rois, int pooled_h,
-                                      int pooled_w, int sampling_ratio, float* out, int32_t* out_levels,
-                                      void* stream) {
-  using namespace b200;
+namespace b200 {
+namespace {
+int roi_align_forward_impl(bool exact, const b200_level* levels, int n_levels, int layout, int batch, int channels,
+                           const float* rois, int64_t n_rois, int pooled_h, int pooled_w, int sampling_ratio,
+                           float* out, int32_t* out_levels, void* stream) {
   B200_REQUIRE(layout == B200_LAYOUT_NCHW || layout == B200_LAYOUT_NHWC, "roi_align: bad layout %d", layout);
   B200_REQUIRE(batch > 0 && channels > 0 && pooled_h > 0 && pooled_w > 0 && n_rois >= 0 && sampling_ratio >= 0,
                "roi_align: bad shape");
@@ -384,8 +384,27 @@ extern "C" int b200_roi_align_forward(const b200_level* levels, int n_levels, in
   int rc = fill_level_table(levels, n_levels, &lt);
   if (rc != B200_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return g_exact ? launch_forward<true>(lt, layout, channels, rois, n_rois, pooled_h, pooled_w, sampling_ratio,
-                                        out, out_levels, st)
-                 : launch_forward<false>(lt, layout, channels, rois, n_rois, pooled_h, pooled_w,
-                                         sampling_ratio, out, out_levels, st);
+  return exact ? launch_forward<true>(lt, layout, channels, rois, n_rois, pooled_h, pooled_w, sampling_ratio, out,
+                                      out_levels, st)
+               : launch_forward<false>(lt, layout, channels, rois, n_rois, pooled_h, pooled_w, sampling_ratio,
+                                       out, out_levels, st);
+}
+}  // namespace
+}  // namespace b200
+
+extern "C" int b200_roi_align_forward(const b200_level* levels, int n_levels, int layout, int batch,
+                                      int channels, const float* rois, int64_t n_rois, int pooled_h,
+                                      int pooled_w, int sampling_ratio, float* out, int32_t* out_levels,
+                                      void* stream) {
+  // g_exact is the tuning hook of b200_debug_set; it is true unless a perf script flipped it
+  return b200::roi_align_forward_impl(b200::g_exact, levels, n_levels, layout, batch, channels, rois, n_rois,
+                                      pooled_h, pooled_w, sampling_ratio, out, out_levels, stream);
+}
+
+extern "C" int b200_roi_align_forward_fast(const b200_level* levels, int n_levels, int layout, int batch,
+                                           int channels, const float* rois, int64_t n_rois, int pooled_h,
+                                           int pooled_w, int sampling_ratio, float* out, int32_t* out_levels,
+                                           void* stream) {
+  return b200::roi_align_forward_impl(false, levels, n_levels, layout, batch, channels, rois, n_rois, pooled_h,
+                                      pooled_w, sampling_ratio, out, out_levels, stream);
 }

@@ -54,6 +54,22 @@ __device__ __forceinline__ void tile_copy_out(const float* out_s, float* __restr
   }
 }
 
+// the reverse: a contiguous [64 x NB] block of global memory into the (shifted) tile
+__device__ __forceinline__ void tile_copy_in(float* tile, const float* __restrict__ src_f, int NB, bool swz, int tid,
+                                             int nthreads) {
+  const float4* src = reinterpret_cast<const float4*>(src_f);
+  float4* dst = reinterpret_cast<float4*>(tile);
+  if (!swz) {
+    for (int i = tid; i < kChunk * NB / 4; i += nthreads) dst[i] = __ldcs(src + i);
+  } else {
+    const int rowv = NB >> 2;
+    for (int i = tid; i < kChunk * rowv; i += nthreads) {
+      const int c = i / rowv;
+      dst[i + (c >> 3)] = __ldcs(src + i);
+    }
+  }
+}
+
 // roi_align_fwd_sep.cu
 int launch_forward_sep(const LevelTable& lt, int C, const float* rois, int64_t n_rois, int PH, int PW, float* out,
                        int32_t* out_levels, int variant, cudaStream_t st);

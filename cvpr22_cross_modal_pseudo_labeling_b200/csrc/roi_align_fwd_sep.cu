@@ -30,13 +30,6 @@
 namespace b200 {
 namespace {
 
-struct XSample {
-  int jhi;     // index (in the CTA's column list) of the sample's right tap column
-  float l, h;  // weights of the right / left tap (left == right column: l = l + h, h = 0)
-  int pad;
-};
-constexpr int kMaxCols = 2 * kMaxAxisSamples;
-
 __device__ __forceinline__ float4 lds128(uint32_t a) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
@@ -91,62 +84,8 @@ roi_align_fwd_sep(const LevelTable lt, int C, const float* __restrict__ rois, in
   const int H = lt.H[h.level], W = lt.W[h.level];
   const RoiGeom g = roi_geometry(h.x1, h.y1, h.x2, h.y2, lt.scale[h.level], PH, PW, 2);
   const int warp = tid >> 5, lane = tid & 31;
-  const int ns = 2 * PW;
 
-  // warp 0: row table.  warp 1: sample table + the list of distinct columns in the order the
-  // march needs them (a sample either reuses the previous columns, shifts by one, or starts
-  // a new pair).
-  if (warp == 0) {
-    bool ok = false;
-    AxisTap t;
-    t.lo = t.hi = 0;
-    t.l = t.h = 0.f;
-    if (lane < 2 * PH) t = axis_sample(g.start_h, lane >> 1, g.bin_h, lane & 1, 2, H, ok);
-    ok = ok && lane < 2 * PH;
-    AxisEntry e;
-    e.lo = ok ? t.lo * W * C : 0;
-    e.hi = ok ? t.hi * W * C : 0;
-    e.l = ok ? t.l : 0.f;
-    e.h = ok ? t.h : 0.f;
-    if (lane < 2 * PH) ytab[lane] = e;
-  } else if (warp == 1) {
-    bool ok = false;
-    AxisTap t;
-    t.lo = t.hi = 0;
-    t.l = t.h = 0.f;
-    if (lane < ns) t = axis_sample(g.start_w, lane >> 1, g.bin_w, lane & 1, 2, W, ok);
-    ok = ok && lane < ns;
-    const int lo = ok ? t.lo * C : 0, hi = ok ? t.hi * C : 0;
-    const int plo = __shfl_up_sync(0xffffffffu, lo, 1), phi = __shfl_up_sync(0xffffffffu, hi, 1);
-    int act = kActLoad2;
-    if (lane > 0) {
-      if (lo == plo && hi == phi) act = kActReuse;
-      else if (lo == phi) act = kActShift;
-    }
-    int nnew = act == kActReuse ? 0 : (act == kActShift ? 1 : (lo == hi ? 1 : 2));
-    if (lane >= ns) nnew = 0;
-    int scan = nnew;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, scan, d);
-      if (lane >= d) scan += v;
-    }
-    if (lane < ns) {
-      XSample e;
-      e.jhi = scan - 1;
-      const float wl = ok ? t.l : 0.f, wh = ok ? t.h : 0.f;
-      e.l = lo == hi ? wl + wh : wl;
-      e.h = lo == hi ? 0.f : wh;
-      e.pad = 0;
-      xs[lane] = e;
-      if (nnew >= 1) colofs[scan - 1] = hi * 4;
-      if (nnew == 2) colofs[scan - 2] = lo * 4;
-    }
-    if (lane == 31) {
-      ncols_s = scan;
-      xs[ns].jhi = -1;  // sentinel: ends the consume loop after the last sample
-    }
-  }
+  build_sep_tables(g, PH, PW, H, W, C, warp, lane, ytab, xs, colofs, &ncols_s);
   __syncthreads();
 
   const int ncols = ncols_s;
@@ -162,23 +101,7 @@ roi_align_fwd_sep(const LevelTable lt, int C, const float* __restrict__ rois, in
   int row[4] = {0, 0, 0, 0};
   float w[4] = {0.f, 0.f, 0.f, 0.f};
   bool use[4] = {false, false, false, false};
-  if (active) {
-    const AxisEntry ya = ytab[2 * ph], yb = ytab[2 * ph + 1];
-    row[0] = ya.lo; row[1] = ya.hi; row[2] = yb.lo; row[3] = yb.hi;
-    w[0] = ya.h; w[1] = ya.l; w[2] = yb.h; w[3] = yb.l;
-    use[0] = use[1] = use[2] = use[3] = true;
-#pragma unroll
-    for (int k = 1; k < 4; ++k) {
-#pragma unroll
-      for (int j = 0; j < k; ++j) {
-        if (use[k] && row[k] == row[j]) {  // the earliest occurrence of a row is never merged away
-          w[j] += w[k];
-          w[k] = 0.f;
-          use[k] = false;
-        }
-      }
-    }
-  }
+  if (active) merge_tap_rows(ytab[2 * ph], ytab[2 * ph + 1], row, w, use);
   const float* img = lt.data[h.level] + (size_t)h.batch * H * W * C + 4 * q;
   const uint32_t xs_a = smem_u32(xs), co_a = smem_u32(colofs);
   const uint32_t tile_a = smem_u32(out_s) + 4u * (uint32_t)(tile_row(4 * q, NB, swz) + ph * PW);
@@ -298,6 +221,8 @@ int launch_forward_sep(const LevelTable& lt, int C, const float* rois, int64_t n
                        int32_t* out_levels, int variant, cudaStream_t st) {
   const int n_chunks = C / kChunk;
   int cpc = n_chunks % 4 == 0 ? 4 : (n_chunks % 2 == 0 ? 2 : 1);
+  // few RoIs (the mask pooler on the kept detections): one chunk per CTA keeps the grid wide
+  if (n_rois < 2048) cpc = 1;
   if (variant & 8) cpc = 1;
   variant &= 7;
 #define B200_SEP(T, MB, KPH, KPW, BUFS, D) \

@@ -135,4 +135,96 @@ __device__ __forceinline__ void build_axis_tables(const RoiGeom& g, int PH, int 
   if (lane < ns) (is_y ? ytab : xtab)[lane] = e;
 }
 
+// ---------------------------------------------------------------------------------------
+// Tables of the separable marching kernels (roi_align_fwd_sep.cu, roi_align_bwd.cu).
+// Rows: AxisEntry per y-sample (element offsets y*W*C).  Columns: the list of DISTINCT tap
+// columns in the order a left-to-right march needs them (byte offsets x*C*4), and per x-sample
+// the list index of its right tap column -- its left tap column is the previous list entry,
+// or the same entry when the sample is clamped to the border (then l carries l + h and h = 0).
+// ---------------------------------------------------------------------------------------
+struct XSample {
+  int jhi;     // index (in the column list) of the sample's right tap column
+  float l, h;  // weights of the right / left tap
+  int pad;
+};
+constexpr int kMaxCols = 2 * kMaxAxisSamples;
+
+// warp 0 fills ytab[2*PH], warp 1 fills xs[2*PW] (+ a sentinel xs[2*PW].jhi = -1), colofs[] and
+// *ncols; the caller synchronises the CTA afterwards.
+__device__ __forceinline__ void build_sep_tables(const RoiGeom& g, int PH, int PW, int H, int W, int C, int warp,
+                                                 int lane, AxisEntry* ytab, XSample* xs, int* colofs, int* ncols) {
+  if (warp == 0) {
+    bool ok = false;
+    AxisTap t;
+    t.lo = t.hi = 0;
+    t.l = t.h = 0.f;
+    if (lane < 2 * PH) t = axis_sample(g.start_h, lane >> 1, g.bin_h, lane & 1, 2, H, ok);
+    ok = ok && lane < 2 * PH;
+    AxisEntry e;
+    e.lo = ok ? t.lo * W * C : 0;
+    e.hi = ok ? t.hi * W * C : 0;
+    e.l = ok ? t.l : 0.f;
+    e.h = ok ? t.h : 0.f;
+    if (lane < 2 * PH) ytab[lane] = e;
+  } else if (warp == 1) {
+    const int ns = 2 * PW;
+    bool ok = false;
+    AxisTap t;
+    t.lo = t.hi = 0;
+    t.l = t.h = 0.f;
+    if (lane < ns) t = axis_sample(g.start_w, lane >> 1, g.bin_w, lane & 1, 2, W, ok);
+    ok = ok && lane < ns;
+    const int lo = ok ? t.lo * C : 0, hi = ok ? t.hi * C : 0;
+    const int plo = __shfl_up_sync(0xffffffffu, lo, 1), phi = __shfl_up_sync(0xffffffffu, hi, 1);
+    int act = kActLoad2;
+    if (lane > 0) {
+      if (lo == plo && hi == phi) act = kActReuse;
+      else if (lo == phi) act = kActShift;
+    }
+    int nnew = act == kActReuse ? 0 : (act == kActShift ? 1 : (lo == hi ? 1 : 2));
+    if (lane >= ns) nnew = 0;
+    int scan = nnew;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, scan, d);
+      if (lane >= d) scan += v;
+    }
+    if (lane < ns) {
+      XSample e;
+      e.jhi = scan - 1;
+      const float wl = ok ? t.l : 0.f, wh = ok ? t.h : 0.f;
+      e.l = lo == hi ? wl + wh : wl;
+      e.h = lo == hi ? 0.f : wh;
+      e.pad = 0;
+      xs[lane] = e;
+      if (nnew >= 1) colofs[scan - 1] = hi * 4;
+      if (nnew == 2) colofs[scan - 2] = lo * 4;
+    }
+    if (lane == 31) {
+      *ncols = scan;
+      xs[ns].jhi = -1;  // sentinel: ends a consume loop after the last sample
+    }
+  }
+}
+
+// Tap rows of one output row (its two y-samples), duplicates merged: weights of equal rows add
+// up and the later duplicate is dropped (use[k] = false, w[k] = 0).
+__device__ __forceinline__ void merge_tap_rows(const AxisEntry& ya, const AxisEntry& yb, int (&row)[4], float (&w)[4],
+                                               bool (&use)[4]) {
+  row[0] = ya.lo; row[1] = ya.hi; row[2] = yb.lo; row[3] = yb.hi;
+  w[0] = ya.h; w[1] = ya.l; w[2] = yb.h; w[3] = yb.l;
+  use[0] = use[1] = use[2] = use[3] = true;
+#pragma unroll
+  for (int k = 1; k < 4; ++k) {
+#pragma unroll
+    for (int j = 0; j < k; ++j) {
+      if (use[k] && row[k] == row[j]) {  // the earliest occurrence of a row is never merged away
+        w[j] += w[k];
+        w[k] = 0.f;
+        use[k] = false;
+      }
+    }
+  }
+}
+
 }  // namespace b200

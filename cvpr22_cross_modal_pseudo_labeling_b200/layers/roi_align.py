@@ -1,6 +1,7 @@
 """RoIAlign entry points mirroring maskrcnn_benchmark.layers.roi_align (reference
 layers/roi_align.py:12-61) plus the fused multi-level form the Pooler uses."""
 import ctypes
+import os
 import weakref
 
 import torch
@@ -10,6 +11,27 @@ from torch.autograd.function import once_differentiable
 from torch.nn.modules.utils import _pair
 
 from .. import _ext
+
+
+MATH_MODES = ("exact", "fast")
+_default_math = os.environ.get("B200_ROI_ALIGN_MATH", "exact")
+if _default_math not in MATH_MODES:
+    raise ValueError("B200_ROI_ALIGN_MATH must be one of %s" % (MATH_MODES,))
+
+
+def set_roi_align_math(mode):
+    """Process-wide default arithmetic of the RoIAlign forward: "exact" reproduces the reference's
+    operation order bit for bit (b200_roi_align_forward); "fast" evaluates the same bilinear sums
+    separably with FMAs (b200_roi_align_forward_fast; <= 1e-5 relative).  Returns the old mode."""
+    global _default_math
+    if mode not in MATH_MODES:
+        raise ValueError("math must be one of %s" % (MATH_MODES,))
+    old, _default_math = _default_math, mode
+    return old
+
+
+def get_roi_align_math():
+    return _default_math
 
 
 def _layout_of(x):
@@ -49,8 +71,11 @@ def _check_inputs(feats, rois):
             raise ValueError("all levels must share batch and channel sizes")
 
 
-def _forward(feats, scales, rois, output_size, sampling_ratio, want_levels=False):
+def _forward(feats, scales, rois, output_size, sampling_ratio, want_levels=False, math=None):
     _check_inputs(feats, rois)
+    math = _default_math if math is None else math
+    if math not in MATH_MODES:
+        raise ValueError("math must be one of %s" % (MATH_MODES,))
     ph, pw = output_size
     rois = rois.float().contiguous()
     lay = [_layout_of(f) for f in feats]
@@ -66,9 +91,9 @@ def _forward(feats, scales, rois, output_size, sampling_ratio, want_levels=False
     if r > 0:
         arr = _levels_array(tensors, scales)
         with torch.cuda.device(dev):
-            rc = _ext.lib().b200_roi_align_forward(arr, len(tensors), layout, feats[0].size(0), c, _ext.ptr(rois),
-                                                   r, ph, pw, int(sampling_ratio), _ext.ptr(out),
-                                                   _ext.ptr(levels_out), _ext.stream_ptr(dev))
+            fn = _ext.lib().b200_roi_align_forward if math == "exact" else _ext.lib().b200_roi_align_forward_fast
+            rc = fn(arr, len(tensors), layout, feats[0].size(0), c, _ext.ptr(rois), r, ph, pw, int(sampling_ratio),
+                    _ext.ptr(out), _ext.ptr(levels_out), _ext.stream_ptr(dev))
         _ext.check(rc, "b200_roi_align_forward")
     return out, levels_out
 
@@ -141,11 +166,11 @@ class _ROIAlignMulti(Function):
     back out to NCHW (backward), so both directions use the marching kernels."""
 
     @staticmethod
-    def forward(ctx, rois, output_size, scales, sampling_ratio, stage, *feats):
+    def forward(ctx, rois, output_size, scales, sampling_ratio, stage, math, *feats):
         output_size = _pair(output_size)
         staged = [bool(stage) and _stageable(f, sampling_ratio) for f in feats]
         run = [nhwc_cache.get(f) if s else f for f, s in zip(feats, staged)]
-        out, _ = _forward(run, scales, rois, output_size, sampling_ratio)
+        out, _ = _forward(run, scales, rois, output_size, sampling_ratio, math=math)
         ctx.save_for_backward(rois.float().contiguous())
         ctx.output_size = output_size
         ctx.scales = tuple(scales)
@@ -176,32 +201,35 @@ class _ROIAlignMulti(Function):
                     g = n
                 out.append(g)
             grads = out
-        return (None, None, None, None, None, *grads)
+        return (None, None, None, None, None, None, *grads)
 
 
-def roi_align_multilevel(feats, rois, output_size, scales, sampling_ratio, stage_nhwc=False):
+def roi_align_multilevel(feats, rois, output_size, scales, sampling_ratio, stage_nhwc=False, math=None):
     """feats: list of [B,C,H_l,W_l]; rois [R,5] -> [R,C,PH,PW] in RoI order.
-    stage_nhwc: run NCHW-contiguous maps through a cached NHWC copy (see _ROIAlignMulti)."""
-    return _ROIAlignMulti.apply(rois, output_size, tuple(scales), sampling_ratio, stage_nhwc, *feats)
+    stage_nhwc: run NCHW-contiguous maps through a cached NHWC copy (see _ROIAlignMulti).
+    math: "exact" | "fast" | None (the process default, see set_roi_align_math)."""
+    return _ROIAlignMulti.apply(rois, output_size, tuple(scales), sampling_ratio, stage_nhwc, math, *feats)
 
 
 def roi_align(input, roi, output_size, spatial_scale, sampling_ratio):
     """Same call as the reference's `roi_align = _ROIAlign.apply` (layers/roi_align.py:48)."""
-    return _ROIAlignMulti.apply(roi, output_size, (spatial_scale,), sampling_ratio, False, input)
+    return _ROIAlignMulti.apply(roi, output_size, (spatial_scale,), sampling_ratio, False, None, input)
 
 
 class ROIAlign(nn.Module):
     """Drop-in for maskrcnn_benchmark.layers.ROIAlign (reference layers/roi_align.py:50-69)."""
 
-    def __init__(self, output_size, spatial_scale, sampling_ratio):
+    def __init__(self, output_size, spatial_scale, sampling_ratio, math=None):
         super(ROIAlign, self).__init__()
         self.output_size = output_size
         self.spatial_scale = spatial_scale
         self.sampling_ratio = sampling_ratio
+        self.math = math  # None: process default (set_roi_align_math)
 
     def forward(self, input, rois):
         # the reference wraps this in amp.float_function: fp32 in, fp32 out
-        return roi_align(input.float(), rois.float(), self.output_size, self.spatial_scale, self.sampling_ratio)
+        return _ROIAlignMulti.apply(rois.float(), self.output_size, (self.spatial_scale,), self.sampling_ratio,
+                                    False, self.math, input.float())
 
     def __repr__(self):
         return "%s(output_size=%s, spatial_scale=%s, sampling_ratio=%s)" % (

@@ -31,13 +31,15 @@ class LevelMapper(object):
 
 
 class Pooler(nn.Module):
-    def __init__(self, output_size, scales, sampling_ratio, stage_nhwc=True):
+    def __init__(self, output_size, scales, sampling_ratio, stage_nhwc=True, math=None):
         """
         output_size (tuple[int] or int), scales (list[float]), sampling_ratio (int):
         as the reference (poolers.py:55-76).
         stage_nhwc: run NCHW-contiguous maps through an NHWC copy cached per tensor (and an NHWC
         gradient buffer laid back out to NCHW in the backward) so the marching kernels are used;
         channels_last inputs are always used in place.
+        math: "exact" (bit-identical to ROIAlign_forward_cpu) | "fast" (separable FMA evaluation,
+        <= 1e-5 relative) | None = the process default (layers.roi_align.set_roi_align_math).
         """
         super(Pooler, self).__init__()
         self.poolers = nn.ModuleList(
@@ -46,6 +48,7 @@ class Pooler(nn.Module):
         self.scales = tuple(float(s) for s in scales)
         self.sampling_ratio = sampling_ratio
         self.stage_nhwc = stage_nhwc
+        self.math = math
         lvl_min = -torch.log2(torch.tensor(scales[0], dtype=torch.float32)).item()
         lvl_max = -torch.log2(torch.tensor(scales[-1], dtype=torch.float32)).item()
         self.map_levels = LevelMapper(lvl_min, lvl_max)
@@ -63,7 +66,7 @@ class Pooler(nn.Module):
         rois = self.convert_to_roi_format(boxes)
         feats = list(x)[: len(self.scales)]
         return roi_align_multilevel(feats, rois, self.output_size, self.scales, self.sampling_ratio,
-                                    stage_nhwc=self.stage_nhwc)
+                                    stage_nhwc=self.stage_nhwc, math=self.math)
 
 
 def make_pooler(cfg, head_name):

@@ -84,6 +84,27 @@ def test_config2_pooler_properties(config2):
     assert torch.allclose(o2, 2.0 * out + o1, rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("res", [7, 14])
+def test_config2_fast_math_within_tolerance(config2, res):
+    """Full size, fast math against the bit-exact kernel (itself pinned to the oracle above):
+    every element within rtol 1e-5 (+ atol 1e-6 on unit-variance features); constants pool to
+    the constant; same level assignment."""
+    from cvpr22_cross_modal_pseudo_labeling_b200.layers.roi_align import _forward
+    feats, rois = config2
+    sub = rois if res == 7 else rois[::4]
+    exact, lv_e = _forward(feats, synth.FPN_SCALES, sub, (res, res), 2, want_levels=True, math="exact")
+    fast, lv_f = _forward(feats, synth.FPN_SCALES, sub, (res, res), 2, want_levels=True, math="fast")
+    assert torch.equal(lv_e, lv_f)
+    err = (fast - exact).abs()
+    bound = 1e-5 * exact.abs() + 1e-6
+    assert bool((err <= bound).all()), float((err - bound).max())
+    del exact, fast, err, bound
+    ones = [torch.full_like(f, 3.0) for f in feats]
+    o1, _ = _forward(ones, synth.FPN_SCALES, sub, (res, res), 2, math="fast")
+    inside = (sub[:, 1] > 40) & (sub[:, 2] > 40) & (sub[:, 3] < 1200) & (sub[:, 4] < 700)
+    assert torch.allclose(o1[inside], torch.full_like(o1[inside], 3.0), rtol=1e-6, atol=0)
+
+
 def test_config2_mask_pooler_and_backward_adjoint(config2):
     """<Pool(x), g> == <x, Pool^T(g)> at full size (the backward is the adjoint of the forward)."""
     from cvpr22_cross_modal_pseudo_labeling_b200.layers.roi_align import _backward, _forward

@@ -1,6 +1,7 @@
 """GPU parity: RoIAlign forward/backward, fused multi-level Pooler, layouts, RoIPool -- through
 the C ABI, against the CPU oracle.  Forward tolerance: bit-exact in the default (exact)
-mode; rtol 1e-5 (+ atol 1e-6) in the FMA mode.  Backward: rtol 1e-5 of the fp64-accumulated
+mode; rtol 1e-5 (+ atol 1e-6 on unit-variance features) in the fast mode
+(b200_roi_align_forward_fast: separable FMA evaluation).  Backward: rtol 1e-5 of the fp64-accumulated
 oracle, scaled per element by the sum of |addends| (atomics reorder fp32 sums)."""
 import numpy as np
 import pytest
@@ -87,6 +88,70 @@ def test_roi_align_forward_fma_mode_tolerance():
     got = roi_align(x, torch.from_numpy(rois).cuda(), (7, 7), 1 / 16, 2).cpu().numpy()
     _ext().debug_set(False, True, 0)
     np.testing.assert_allclose(got, want, rtol=RTOL, atol=1e-6)
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("nhwc", [False, True])
+def test_roi_align_forward_fast_math(case, nhwc):
+    """b200_roi_align_forward_fast on every shape class: the separable marching kernel (NHWC,
+    sampling_ratio 2) and the FMA-contracted generic gather (everything else)."""
+    from cvpr22_cross_modal_pseudo_labeling_b200.layers.roi_align import _forward
+    b, c, h, w, scale, ph, pw, sr, n = case
+    rng = np.random.default_rng(hash(case) % 2**31 + 1)
+    x = _feat(rng, b, c, h, w, nhwc)
+    rois = _rand_rois(rng, n, b, int(w / scale), int(h / scale))
+    rois[:3, 3] = rois[:3, 1] - 7
+    rois[3:6, 1:] += 5000
+    rois[6, 1:] = [-30.0, -30.0, 40.0, 50.0]                # straddles the top-left corner (clamped taps)
+    rois[7, 1:] = [w / scale - 20, h / scale - 20, w / scale + 60, h / scale + 60]   # bottom-right corner
+    want = oracle.roi_align_forward(x.cpu().contiguous().numpy(), rois, scale, ph, pw, sr)
+    got, _ = _forward([x], (scale,), torch.from_numpy(rois).cuda(), (ph, pw), sr, math="fast")
+    got = got.cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=1e-6)
+    assert np.all(got[3:6] == 0)
+
+
+@pytest.mark.parametrize("res", [7, 14])
+@pytest.mark.parametrize("channels", [64, 128, 192, 256])
+def test_pooler_multilevel_fast_math(res, channels):
+    """Pooler(math="fast") over the pyramid: levels identical, values within 1e-5 of the oracle;
+    192 channels = 3 chunks exercises the one-chunk-per-CTA grid, 128 / 256 the 2- / 4-chunk CTAs."""
+    from cvpr22_cross_modal_pseudo_labeling_b200.modeling import Pooler
+    from cvpr22_cross_modal_pseudo_labeling_b200.structures import BoxList
+    rng = np.random.default_rng(170 + res + channels)
+    b, n = 2, 120
+    feats = _pyramid(rng, b, channels, True)
+    rois = synth.make_rois(rng, n, b)
+    boxes = [BoxList(torch.from_numpy(rois[i * n:(i + 1) * n, 1:]).cuda(), (synth.IMG_W, synth.IMG_H)) for i in range(b)]
+    got = Pooler((res, res), synth.FPN_SCALES, 2, math="fast")(feats, boxes).cpu().numpy()
+    want, _ = oracle.pooler_forward([f.cpu().contiguous().numpy() for f in feats], rois, synth.FPN_SCALES, res, res, 2)
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=1e-6)
+
+
+def test_roi_align_math_default_and_autograd():
+    """set_roi_align_math switches the process default; the fast forward feeds the same backward."""
+    from cvpr22_cross_modal_pseudo_labeling_b200.layers import ROIAlign, get_roi_align_math, roi_align, set_roi_align_math
+    rng = np.random.default_rng(5)
+    x = _feat(rng, 1, 64, 50, 84, True)
+    rois = torch.from_numpy(_rand_rois(rng, 50, 1, 1333, 800)).cuda()
+    assert get_roi_align_math() == "exact"
+    exact = roi_align(x, rois, (7, 7), 1 / 16, 2)
+    old = set_roi_align_math("fast")
+    try:
+        fast = roi_align(x, rois, (7, 7), 1 / 16, 2)
+    finally:
+        set_roi_align_math(old)
+    assert get_roi_align_math() == "exact"
+    assert not torch.equal(exact, fast)                     # different summation order ...
+    assert torch.allclose(exact, fast, rtol=RTOL, atol=1e-6)   # ... same numbers
+    assert torch.equal(ROIAlign((7, 7), 1 / 16, 2, math="fast")(x, rois), fast)
+    with pytest.raises(ValueError):
+        set_roi_align_math("sloppy")
+    xg = x.clone().requires_grad_(True)
+    ROIAlign((7, 7), 1 / 16, 2, math="fast")(xg, rois).sum().backward()
+    xe = x.clone().requires_grad_(True)
+    ROIAlign((7, 7), 1 / 16, 2, math="exact")(xe, rois).sum().backward()
+    assert torch.allclose(xg.grad, xe.grad, rtol=1e-5, atol=1e-5)   # same kernel; atomics reorder the sums
 
 
 def test_roi_align_known_answers():
