@@ -117,6 +117,18 @@ __device__ void generic_roi(const float* __restrict__ feat, int C, int H, int W,
   }
 }
 
+// mean over the bins of each (RoI, channel) row of an already pooled block (generic path only:
+// the marching kernels produce it from their shared-memory tile)
+__global__ void __launch_bounds__(256) pooled_mean_kernel(const float* __restrict__ pooled, long long rows, int NB,
+                                                          float* __restrict__ mean) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  const float* p = pooled + i * NB;
+  float s = 0.f;
+  for (int k = 0; k < NB; ++k) s = __fadd_rn(s, p[k]);
+  mean[i] = __fdiv_rn(s, (float)NB);
+}
+
 // grid.x = n_rois * ceil(C / c_per_cta)
 template <bool kExact, int kLayout>
 __global__ void __launch_bounds__(256)
@@ -190,7 +202,7 @@ __device__ __forceinline__ void sample_pair(const Vec<V> (&Lc)[4], const Vec<V> 
 template <bool kExact, int kThreads, int kMinBlocks, int V>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 roi_align_fwd_march(const LevelTable lt, int C, const float* __restrict__ rois, int PH, int PW,
-                    float* __restrict__ out, int32_t* __restrict__ out_levels) {
+                    float* __restrict__ out, float* __restrict__ out_mean, int32_t* __restrict__ out_levels) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int NB = PH * PW;
   const bool swz = (NB & 3) == 0;
@@ -208,6 +220,7 @@ roi_align_fwd_march(const LevelTable lt, int C, const float* __restrict__ rois, 
   if (ck == 0 && tid == 0 && out_levels) out_levels[r] = h.level;
   if (h.level < 0) {
     zero_fill(out_roi + (size_t)c_begin * NB, kChunk * NB, tid, kThreads);
+    if (out_mean) zero_fill(out_mean + (size_t)r * C + c_begin, kChunk, tid, kThreads);
     return;
   }
   const int H = lt.H[h.level], W = lt.W[h.level];
@@ -275,6 +288,7 @@ roi_align_fwd_march(const LevelTable lt, int C, const float* __restrict__ rois, 
   __syncthreads();
   // ---- contiguous [64 x NB] block of the NCHW output ------------------------------------
   tile_copy_out(out_s, out_roi + (size_t)c_begin * NB, NB, swz, tid, kThreads);
+  if (out_mean) tile_mean_out(out_s, out_mean + (size_t)r * C + c_begin, NB, swz, tid);
 }
 
 size_t march_smem_bytes(int NB) {
@@ -287,36 +301,36 @@ int g_variant = 0;  // tuning hook: occupancy variant of the marching kernel
 
 template <bool kExact, int kThreads, int kMinBlocks, int V>
 int launch_march(const LevelTable& lt, int C, const float* rois, int64_t n_rois, int PH, int PW, float* out,
-                 int32_t* out_levels, cudaStream_t st) {
+                 float* out_mean, int32_t* out_levels, cudaStream_t st) {
   const size_t smem = march_smem_bytes(PH * PW);
   auto kern = roi_align_fwd_march<kExact, kThreads, kMinBlocks, V>;
   static SmemHighWater hw;  // one per template instantiation
   int rc = ensure_dynamic_smem(kern, smem, &hw, "roi_align: smem attribute");
   if (rc != B200_OK) return rc;
   const int64_t grid = n_rois * (C / kChunk);
-  kern<<<(unsigned)grid, kThreads, smem, st>>>(lt, C, rois, PH, PW, out, out_levels);
+  kern<<<(unsigned)grid, kThreads, smem, st>>>(lt, C, rois, PH, PW, out, out_mean, out_levels);
   B200_CHECK_LAUNCH("roi_align_fwd_march");
   return B200_OK;
 }
 
 template <bool kExact>
 int launch_forward(const LevelTable& lt, int layout, int C, const float* rois, int64_t n_rois, int PH, int PW,
-                   int sr, float* out, int32_t* out_levels, cudaStream_t st) {
+                   int sr, float* out, float* out_mean, int32_t* out_levels, cudaStream_t st) {
   const int NB = PH * PW;
   const bool march_ok = !g_force_generic && layout == B200_LAYOUT_NHWC && sr == 2 && PH <= 16 && PW <= 16 &&
                         C % kChunk == 0 && (NB * kChunk) % 4 == 0;
   B200_REQUIRE(n_rois * ((C + 15) / 16) < (int64_t)1 << 31, "roi_align: too many RoIs for one launch");
-  if (march_ok && !kExact) return launch_forward_sep(lt, C, rois, n_rois, PH, PW, out, out_levels, g_variant, st);
+  if (march_ok && !kExact) return launch_forward_sep(lt, C, rois, n_rois, PH, PW, out, out_mean, out_levels, g_variant, st);
   if (march_ok) {
     // g_variant (tuning hook): CTAs/SM = 6 (default) / 5 / 4 for 128 threads, 3 / 3 / 2 for 256.
     // (2 channels per lane with twice the warps was measured 35-55 % slower: V stays 4.)
     if (PH * (kChunk / 4) <= 128) {
-      if (g_variant == 1) return launch_march<kExact, 128, 5, 4>(lt, C, rois, n_rois, PH, PW, out, out_levels, st);
-      if (g_variant == 2) return launch_march<kExact, 128, 4, 4>(lt, C, rois, n_rois, PH, PW, out, out_levels, st);
-      return launch_march<kExact, 128, 6, 4>(lt, C, rois, n_rois, PH, PW, out, out_levels, st);
+      if (g_variant == 1) return launch_march<kExact, 128, 5, 4>(lt, C, rois, n_rois, PH, PW, out, out_mean, out_levels, st);
+      if (g_variant == 2) return launch_march<kExact, 128, 4, 4>(lt, C, rois, n_rois, PH, PW, out, out_mean, out_levels, st);
+      return launch_march<kExact, 128, 6, 4>(lt, C, rois, n_rois, PH, PW, out, out_mean, out_levels, st);
     }
-    if (g_variant == 2) return launch_march<kExact, 256, 2, 4>(lt, C, rois, n_rois, PH, PW, out, out_levels, st);
-    return launch_march<kExact, 256, 3, 4>(lt, C, rois, n_rois, PH, PW, out, out_levels, st);
+    if (g_variant == 2) return launch_march<kExact, 256, 2, 4>(lt, C, rois, n_rois, PH, PW, out, out_mean, out_levels, st);
+    return launch_march<kExact, 256, 3, 4>(lt, C, rois, n_rois, PH, PW, out, out_mean, out_levels, st);
   }
   // generic: pick channels per CTA so that a CTA has >= ~2k units of work
   int c_per_cta = C;
@@ -337,6 +351,11 @@ int launch_forward(const LevelTable& lt, int layout, int C, const float* rois, i
     roi_align_fwd_generic<kExact, B200_LAYOUT_NCHW>
         <<<(unsigned)grid, 256, 0, st>>>(lt, C, rois, PH, PW, sr, c_per_cta, n_cchunks, out, out_levels);
   B200_CHECK_LAUNCH("roi_align_fwd_generic");
+  if (out_mean) {
+    const int64_t rows = n_rois * C;
+    pooled_mean_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(out, rows, NB, out_mean);
+    B200_CHECK_LAUNCH("pooled_mean_kernel");
+  }
   return B200_OK;
 }
 
@@ -373,7 +392,7 @@ namespace b200 {
 namespace {
 int roi_align_forward_impl(bool exact, const b200_level* levels, int n_levels, int layout, int batch, int channels,
                            const float* rois, int64_t n_rois, int pooled_h, int pooled_w, int sampling_ratio,
-                           float* out, int32_t* out_levels, void* stream) {
+                           float* out, float* out_mean, int32_t* out_levels, void* stream) {
   B200_REQUIRE(layout == B200_LAYOUT_NCHW || layout == B200_LAYOUT_NHWC, "roi_align: bad layout %d", layout);
   B200_REQUIRE(batch > 0 && channels > 0 && pooled_h > 0 && pooled_w > 0 && n_rois >= 0 && sampling_ratio >= 0,
                "roi_align: bad shape");
@@ -385,9 +404,9 @@ int roi_align_forward_impl(bool exact, const b200_level* levels, int n_levels, i
   if (rc != B200_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return exact ? launch_forward<true>(lt, layout, channels, rois, n_rois, pooled_h, pooled_w, sampling_ratio, out,
-                                      out_levels, st)
+                                      out_mean, out_levels, st)
                : launch_forward<false>(lt, layout, channels, rois, n_rois, pooled_h, pooled_w, sampling_ratio,
-                                       out, out_levels, st);
+                                       out, out_mean, out_levels, st);
 }
 }  // namespace
 }  // namespace b200
@@ -398,7 +417,7 @@ extern "C" int b200_roi_align_forward(const b200_level* levels, int n_levels, in
                                       void* stream) {
   // g_exact is the tuning hook of b200_debug_set; it is true unless a perf script flipped it
   return b200::roi_align_forward_impl(b200::g_exact, levels, n_levels, layout, batch, channels, rois, n_rois,
-                                      pooled_h, pooled_w, sampling_ratio, out, out_levels, stream);
+                                      pooled_h, pooled_w, sampling_ratio, out, nullptr, out_levels, stream);
 }
 
 extern "C" int b200_roi_align_forward_fast(const b200_level* levels, int n_levels, int layout, int batch,
@@ -406,5 +425,14 @@ extern "C" int b200_roi_align_forward_fast(const b200_level* levels, int n_level
                                            int pooled_w, int sampling_ratio, float* out, int32_t* out_levels,
                                            void* stream) {
   return b200::roi_align_forward_impl(false, levels, n_levels, layout, batch, channels, rois, n_rois, pooled_h,
-                                      pooled_w, sampling_ratio, out, out_levels, stream);
+                                      pooled_w, sampling_ratio, out, nullptr, out_levels, stream);
+}
+
+extern "C" int b200_roi_align_forward_ex(const b200_level* levels, int n_levels, int layout, int batch, int channels,
+                                         const float* rois, int64_t n_rois, int pooled_h, int pooled_w,
+                                         int sampling_ratio, int math, float* out, float* out_mean,
+                                         int32_t* out_levels, void* stream) {
+  B200_REQUIRE(math == B200_ROI_MATH_EXACT || math == B200_ROI_MATH_FAST, "roi_align: bad math mode %d", math);
+  return b200::roi_align_forward_impl(math == B200_ROI_MATH_EXACT, levels, n_levels, layout, batch, channels, rois,
+                                      n_rois, pooled_h, pooled_w, sampling_ratio, out, out_mean, out_levels, stream);
 }

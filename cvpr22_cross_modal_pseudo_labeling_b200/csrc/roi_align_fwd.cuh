@@ -54,6 +54,19 @@ __device__ __forceinline__ void tile_copy_out(const float* out_s, float* __restr
   }
 }
 
+// Per-channel mean over the bins of the tile (nn.AvgPool2d(kernel_size = pooled size) of the
+// pooled block, roi_box_predictors.py:16-17,:62): sequential fp32 sum in bin order, then one
+// division, as torch's avg_pool2d kernel does.  Threads 0..63, one channel each; bank-conflict
+// free for odd NB, 2-way otherwise.
+__device__ __forceinline__ void tile_mean_out(const float* tile, float* __restrict__ mean, int NB, bool swz, int tid) {
+  if (tid < kChunk) {
+    const float* row = tile + tile_row(tid, NB, swz);
+    float s = 0.f;
+    for (int i = 0; i < NB; ++i) s = __fadd_rn(s, row[i]);
+    mean[tid] = __fdiv_rn(s, (float)NB);
+  }
+}
+
 // the reverse: a contiguous [64 x NB] block of global memory into the (shifted) tile
 __device__ __forceinline__ void tile_copy_in(float* tile, const float* __restrict__ src_f, int NB, bool swz, int tid,
                                              int nthreads) {
@@ -72,6 +85,6 @@ __device__ __forceinline__ void tile_copy_in(float* tile, const float* __restric
 
 // roi_align_fwd_sep.cu
 int launch_forward_sep(const LevelTable& lt, int C, const float* rois, int64_t n_rois, int PH, int PW, float* out,
-                       int32_t* out_levels, int variant, cudaStream_t st);
+                       float* out_mean, int32_t* out_levels, int variant, cudaStream_t st);
 
 }  // namespace b200

@@ -58,7 +58,8 @@ __device__ __forceinline__ float4 fma4(float w, float4 v, float4 a) {
 template <int kThreads, int kMinBlocks, int kPH, int kPW, int kBufs, int kDepth>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 roi_align_fwd_sep(const LevelTable lt, int C, const float* __restrict__ rois, int PH_rt, int PW_rt,
-                  int chunks_per_cta, float* __restrict__ out, int32_t* __restrict__ out_levels) {
+                  int chunks_per_cta, float* __restrict__ out, float* __restrict__ out_mean,
+                  int32_t* __restrict__ out_levels) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int PH = kPH > 0 ? kPH : PH_rt, PW = kPW > 0 ? kPW : PW_rt;
   const int NB = PH * PW;
@@ -79,6 +80,7 @@ roi_align_fwd_sep(const LevelTable lt, int C, const float* __restrict__ rois, in
   if (c0 == 0 && tid == 0 && out_levels) out_levels[r] = h.level;
   if (h.level < 0) {
     zero_fill(out_roi + (size_t)c0 * NB, chunks_per_cta * kChunk * NB, tid, kThreads);
+    if (out_mean) zero_fill(out_mean + (size_t)r * C + c0, chunks_per_cta * kChunk, tid, kThreads);
     return;
   }
   const int H = lt.H[h.level], W = lt.W[h.level];
@@ -187,6 +189,7 @@ roi_align_fwd_sep(const LevelTable lt, int C, const float* __restrict__ rois, in
     }
     __syncthreads();
     tile_copy_out(out_s + buf * tile_floats, out_roi + (size_t)c_begin * NB, NB, swz, tid, kThreads);
+    if (out_mean) tile_mean_out(out_s + buf * tile_floats, out_mean + (size_t)r * C + c_begin, NB, swz, tid);
     // one tile: everyone must be done reading it before the next chunk's stores.  Two tiles:
     // the next chunk writes the other one, and the barrier after THAT chunk orders its
     // copy-out before this tile is written again.
@@ -201,14 +204,14 @@ size_t sep_smem_bytes(int NB, int bufs) {
 
 template <int kThreads, int kMinBlocks, int kPH, int kPW, int kBufs, int kDepth>
 int launch_sep(const LevelTable& lt, int C, const float* rois, int64_t n_rois, int PH, int PW, int chunks_per_cta,
-               float* out, int32_t* out_levels, cudaStream_t st) {
+               float* out, float* out_mean, int32_t* out_levels, cudaStream_t st) {
   const size_t smem = sep_smem_bytes(PH * PW, kBufs);
   auto kern = roi_align_fwd_sep<kThreads, kMinBlocks, kPH, kPW, kBufs, kDepth>;
   static SmemHighWater hw;  // one per template instantiation
   int rc = ensure_dynamic_smem(kern, smem, &hw, "roi_align: smem attribute");
   if (rc != B200_OK) return rc;
   const int64_t grid = n_rois * (C / (kChunk * chunks_per_cta));
-  kern<<<(unsigned)grid, kThreads, smem, st>>>(lt, C, rois, PH, PW, chunks_per_cta, out, out_levels);
+  kern<<<(unsigned)grid, kThreads, smem, st>>>(lt, C, rois, PH, PW, chunks_per_cta, out, out_mean, out_levels);
   B200_CHECK_LAUNCH("roi_align_fwd_sep");
   return B200_OK;
 }
@@ -218,7 +221,7 @@ int launch_sep(const LevelTable& lt, int C, const float* rois, int64_t n_rois, i
 // Preconditions (checked by the caller): NHWC, sampling_ratio 2, PH, PW <= 16, C % 64 == 0,
 // (PH * PW * 64) % 4 == 0.  `variant` is the tuning hook of b200_debug_set.
 int launch_forward_sep(const LevelTable& lt, int C, const float* rois, int64_t n_rois, int PH, int PW, float* out,
-                       int32_t* out_levels, int variant, cudaStream_t st) {
+                       float* out_mean, int32_t* out_levels, int variant, cudaStream_t st) {
   const int n_chunks = C / kChunk;
   int cpc = n_chunks % 4 == 0 ? 4 : (n_chunks % 2 == 0 ? 2 : 1);
   // few RoIs (the mask pooler on the kept detections): one chunk per CTA keeps the grid wide
@@ -226,7 +229,7 @@ int launch_forward_sep(const LevelTable& lt, int C, const float* rois, int64_t n
   if (variant & 8) cpc = 1;
   variant &= 7;
 #define B200_SEP(T, MB, KPH, KPW, BUFS, D) \
-  return launch_sep<T, MB, KPH, KPW, BUFS, D>(lt, C, rois, n_rois, PH, PW, cpc, out, out_levels, st)
+  return launch_sep<T, MB, KPH, KPW, BUFS, D>(lt, C, rois, n_rois, PH, PW, cpc, out, out_mean, out_levels, st)
   // Measured on B200 (scripts/probe_sep.py, B=16 x 1000 RoIs, C=256): one column in flight per
   // thread at 8 CTAs/SM (7x7) / 4 CTAs/SM (14x14) is fastest; two columns in flight or a second
   // output tile cost registers / shared memory, i.e. resident warps, and lose 5-15 %.

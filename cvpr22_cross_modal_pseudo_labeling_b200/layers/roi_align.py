@@ -71,7 +71,9 @@ def _check_inputs(feats, rois):
             raise ValueError("all levels must share batch and channel sizes")
 
 
-def _forward(feats, scales, rois, output_size, sampling_ratio, want_levels=False, math=None):
+def _forward(feats, scales, rois, output_size, sampling_ratio, want_levels=False, math=None, mean_out=None):
+    """-> (pooled [R,C,PH,PW], levels or None).  mean_out: optional preallocated [R,C] fp32 tensor that
+    receives the per-channel mean over the bins (b200_roi_align_forward_ex, fused AvgPool2d)."""
     _check_inputs(feats, rois)
     math = _default_math if math is None else math
     if math not in MATH_MODES:
@@ -91,9 +93,18 @@ def _forward(feats, scales, rois, output_size, sampling_ratio, want_levels=False
     if r > 0:
         arr = _levels_array(tensors, scales)
         with torch.cuda.device(dev):
-            fn = _ext.lib().b200_roi_align_forward if math == "exact" else _ext.lib().b200_roi_align_forward_fast
-            rc = fn(arr, len(tensors), layout, feats[0].size(0), c, _ext.ptr(rois), r, ph, pw, int(sampling_ratio),
-                    _ext.ptr(out), _ext.ptr(levels_out), _ext.stream_ptr(dev))
+            if mean_out is not None:
+                if (mean_out.shape != (r, c) or mean_out.dtype != torch.float32 or not mean_out.is_contiguous()
+                        or mean_out.device != dev):
+                    raise ValueError("mean_out must be a contiguous float32 [R,C] tensor on the input's device")
+                rc = _ext.lib().b200_roi_align_forward_ex(
+                    arr, len(tensors), layout, feats[0].size(0), c, _ext.ptr(rois), r, ph, pw, int(sampling_ratio),
+                    MATH_MODES.index(math), _ext.ptr(out), _ext.ptr(mean_out), _ext.ptr(levels_out),
+                    _ext.stream_ptr(dev))
+            else:
+                fn = _ext.lib().b200_roi_align_forward if math == "exact" else _ext.lib().b200_roi_align_forward_fast
+                rc = fn(arr, len(tensors), layout, feats[0].size(0), c, _ext.ptr(rois), r, ph, pw,
+                        int(sampling_ratio), _ext.ptr(out), _ext.ptr(levels_out), _ext.stream_ptr(dev))
         _ext.check(rc, "b200_roi_align_forward")
     return out, levels_out
 
@@ -209,6 +220,16 @@ def roi_align_multilevel(feats, rois, output_size, scales, sampling_ratio, stage
     stage_nhwc: run NCHW-contiguous maps through a cached NHWC copy (see _ROIAlignMulti).
     math: "exact" | "fast" | None (the process default, see set_roi_align_math)."""
     return _ROIAlignMulti.apply(rois, output_size, tuple(scales), sampling_ratio, stage_nhwc, math, *feats)
+
+
+def roi_align_with_mean(feats, rois, output_size, scales, sampling_ratio, math=None):
+    """Inference-only fused pooler + AvgPool2d(pooled size): -> (pooled [R,C,PH,PW], mean [R,C]).
+    The mean is what FastRCNNPredictor.forward's avgpool (roi_box_predictors.py:62) computes from
+    the pooled block; here it leaves the pooler's shared-memory tile directly."""
+    feats = list(feats)
+    mean = torch.empty((rois.size(0), feats[0].size(1)), dtype=torch.float32, device=feats[0].device)
+    out, _ = _forward(feats, scales, rois, _pair(output_size), sampling_ratio, math=math, mean_out=mean)
+    return out, mean
 
 
 def roi_align(input, roi, output_size, spatial_scale, sampling_ratio):

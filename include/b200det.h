@@ -102,6 +102,22 @@ int b200_roi_align_forward_fast(const b200_level* levels, int n_levels, int layo
                                 int32_t* out_levels, void* stream);
 
 /*
+ * Extended forward: arithmetic selected per call, plus an optional second output
+ *   out_mean [n_rois, channels] fp32 (may be NULL): the mean over the pooled_h*pooled_w bins of
+ *   every (RoI, channel) -- nn.AvgPool2d(kernel_size = pooled size) of the pooled block, the first
+ *   step of FastRCNNPredictor.forward (modeling/roi_heads/box_head/roi_box_predictors.py:16-17, :62)
+ *   -- taken from the output tile while it is still in shared memory, so the pooled block is not
+ *   read back from HBM for it.  Sequential fp32 sum in bin order, one division (torch's order).
+ */
+#define B200_ROI_MATH_EXACT 0
+#define B200_ROI_MATH_FAST 1
+int b200_roi_align_forward_ex(const b200_level* levels, int n_levels, int layout,
+                              int batch, int channels, const float* rois,
+                              int64_t n_rois, int pooled_h, int pooled_w,
+                              int sampling_ratio, int math, float* out,
+                              float* out_mean, int32_t* out_levels, void* stream);
+
+/*
  * Fused multi-level RoIAlign backward (gradient w.r.t. the features).
  * Replaces _C.roi_align_backward (csrc/ROIAlign.h:27-45; kernel
  * csrc/cuda/ROIAlign_cuda.cu:178-254, host :302-346) for every level at once.

@@ -22,7 +22,12 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio"]
+        "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+        "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
+        "l1tex__m_l1tex2xbar_req_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sectors_srcunit_tex_op_red.sum"]
 
 
 def raw(rep):
@@ -65,7 +70,7 @@ def main():
                         if k in rec and rec[k] != "":
                             f.write("  %-90s %s %s\n" % (k, rec[k], units.get(k, "")))
                     f.write("\n")
-            if "roi_align" in name and recs:
+            if "roi_align_fwd_sep" in name and recs:
                 rec = recs[0]
                 conv = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}
                 rd = float(rec["dram__bytes_read.sum"]) * conv[units["dram__bytes_read.sum"]]

@@ -154,6 +154,27 @@ def test_roi_align_math_default_and_autograd():
     assert torch.allclose(xg.grad, xe.grad, rtol=1e-5, atol=1e-5)   # same kernel; atomics reorder the sums
 
 
+@pytest.mark.parametrize("math", ["exact", "fast"])
+@pytest.mark.parametrize("res", [7, 14])
+@pytest.mark.parametrize("nhwc", [False, True])
+def test_roi_align_fused_channel_mean(math, res, nhwc):
+    """b200_roi_align_forward_ex's second output equals AvgPool2d(res) of the pooled block
+    (roi_box_predictors.py:16-17,:62) -- marching kernels (NHWC) and generic path (NCHW)."""
+    from cvpr22_cross_modal_pseudo_labeling_b200.layers import roi_align_with_mean
+    from cvpr22_cross_modal_pseudo_labeling_b200.layers.roi_align import _forward
+    rng = np.random.default_rng(31 + res)
+    feats = _pyramid(rng, 2, 128, nhwc)
+    rois = torch.from_numpy(synth.make_rois(rng, 90, 2)).cuda()
+    pooled, mean = roi_align_with_mean(feats, rois, (res, res), synth.FPN_SCALES, 2, math=math)
+    plain, _ = _forward(feats, synth.FPN_SCALES, rois, (res, res), 2, math=math)
+    assert torch.equal(pooled, plain)                       # the extra output does not disturb the pooled block
+    want = torch.nn.functional.avg_pool2d(pooled, res).flatten(1)
+    assert mean.shape == want.shape
+    assert torch.allclose(mean, want, rtol=1e-6, atol=1e-7)
+    with pytest.raises(ValueError):
+        _forward(feats, synth.FPN_SCALES, rois, (res, res), 2, mean_out=torch.empty((3, 3), device="cuda"))
+
+
 def test_roi_align_known_answers():
     from cvpr22_cross_modal_pseudo_labeling_b200.layers import roi_align
     x = torch.arange(2 * 6 * 6, dtype=torch.float32, device="cuda").reshape(1, 2, 6, 6)
