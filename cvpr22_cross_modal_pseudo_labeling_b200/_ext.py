@@ -40,6 +40,9 @@ SIGNATURES = {
     "b200_nhwc_to_nchw": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "b200_nms_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "b200_nms_batched": (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _f, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "b200_box_candidates": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _f, _f, _f, _f, _f, _i64,
+                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200_select_detections": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "b200_select_topk": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _i, _vp, _vp, _vp, _vp]),
     "b200_embed_match": (_i, [_vp, _vp, _i64, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200_colmax_decode": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),

@@ -4,12 +4,17 @@
 The per-class Python loop of filter_results (reference :135-149, one boxlist_nms call per
 (image, class)) becomes ONE batched NMS over all (image, class) segments; candidates are
 listed class-major / RoI-ascending exactly as the reference enumerates them, so results
-come out in the same order.
+come out in the same order.  Decode + clip + threshold + compaction before the NMS and the
+top-`detections_per_img` selection after it are one library call each (b200_box_candidates,
+b200_select_detections): the forward issues 5 kernels and synchronises the host once.
 """
+import math
+
 import torch
 import torch.nn.functional as F
 from torch import nn
 
+from .... import _ext
 from ....layers import nms_batched
 from ....structures import BoxList
 from ...box_coder import BoxCoder
@@ -40,10 +45,14 @@ class PostProcessor(nn.Module):
         image_shapes = [b.size for b in boxes]
         boxes_per_image = [len(b) for b in boxes]
         concat_boxes = torch.cat([b.bbox for b in boxes], dim=0)
+        num_classes = class_prob.shape[1]
+        teacher_path = self.bbox_aug_enabled or self.is_teacher
+        if not teacher_path and not self.gt_box_eval and self._fused_ok(class_prob, box_regression, num_classes):
+            return self._filter_fused(class_prob, box_regression, concat_boxes, boxes_per_image, image_shapes,
+                                      num_classes)
         if self.cls_agnostic_bbox_reg:
             box_regression = box_regression[:, -4:]
         proposals = self.box_coder.decode(box_regression.view(sum(boxes_per_image), -1), concat_boxes)
-        num_classes = class_prob.shape[1]
         # clip_to_image per image (reference :96, bounding_box.py:214-224)
         lim = torch.cat([torch.tensor([[w - 1, h - 1, w - 1, h - 1]], dtype=proposals.dtype).expand(n, 4)
                          for (w, h), n in zip(image_shapes, boxes_per_image)], dim=0).to(proposals.device)
@@ -73,6 +82,84 @@ class PostProcessor(nn.Module):
                 results.append(bl)
             return results
         return self._filter_batched(proposals, class_prob, boxes_per_image, image_shapes, num_classes)
+
+    def _fused_ok(self, class_prob, box_regression, num_classes):
+        """The library path covers fp32 CUDA inputs, the stock dw/dh clamp and <= 2048 foreground classes."""
+        clip = getattr(self.box_coder, "bbox_xform_clip", math.log(1000. / 16))
+        return (class_prob.is_cuda and class_prob.dtype == torch.float32 and box_regression.dtype == torch.float32
+                and 2 <= num_classes <= 2049 and abs(clip - math.log(1000. / 16)) < 1e-9
+                and (self.cls_agnostic_bbox_reg or box_regression.shape[1] >= 4 * num_classes))
+
+    def _filter_fused(self, class_prob, box_regression, concat_boxes, boxes_per_image, image_shapes, num_classes):
+        """decode + clip + `score > thresh` + per-class compaction (b200_box_candidates) -> batched NMS ->
+        per-image top detections_per_img with the kthvalue tie rule (b200_select_detections).
+        Reference :69-76, :96, :121-163.  One host synchronisation, at the end, sizes the results."""
+        device = class_prob.device
+        n_img, r_total, cfg = len(boxes_per_image), sum(boxes_per_image), num_classes - 1
+        if r_total == 0:
+            return [self._empty(shape, device) for shape in image_shapes]
+        probs = class_prob.contiguous()
+        reg = box_regression.reshape(r_total, -1).contiguous()
+        rois = concat_boxes.to(torch.float32).contiguous()
+        offs = [0]
+        for n in boxes_per_image:
+            offs.append(offs[-1] + n)
+        roi_off = torch.tensor(offs, dtype=torch.int32).to(device, non_blocking=True)
+        sizes = torch.tensor([[float(w), float(h)] for (w, h) in image_shapes], dtype=torch.float32).to(
+            device, non_blocking=True)
+        # softmax rows sum to 1: at most ceil(1/thresh) - 1 classes of a RoI can exceed thresh
+        per_roi = cfg if self.score_thresh <= 0 else min(cfg, max(1, int(math.ceil(1.0 / self.score_thresh)) - 1))
+        cap = r_total * per_roi
+        n_seg = n_img * cfg
+        seg_len = torch.empty((n_seg,), dtype=torch.int32, device=device)
+        seg_off = torch.empty((n_seg + 1,), dtype=torch.int32, device=device)
+        cand_boxes = torch.empty((cap, 4), dtype=torch.float32, device=device)
+        cand_scores = torch.empty((cap,), dtype=torch.float32, device=device)
+        cand_roi = torch.empty((cap,), dtype=torch.int32, device=device)
+        status = torch.empty((2,), dtype=torch.int32, device=device)
+        wx, wy, ww, wh = [float(v) for v in self.box_coder.weights]
+        lib = _ext.lib()
+        with torch.cuda.device(device):
+            st = _ext.stream_ptr(device)
+            rc = lib.b200_box_candidates(_ext.ptr(probs), _ext.ptr(reg), _ext.ptr(rois), _ext.ptr(roi_off),
+                                         _ext.ptr(sizes), n_img, r_total, num_classes, reg.shape[1],
+                                         int(bool(self.cls_agnostic_bbox_reg)), wx, wy, ww, wh,
+                                         float(self.score_thresh), cap, _ext.ptr(seg_len), _ext.ptr(seg_off),
+                                         _ext.ptr(cand_boxes), _ext.ptr(cand_scores), _ext.ptr(cand_roi),
+                                         _ext.ptr(status), st)
+            _ext.check(rc, "b200_box_candidates")
+            if self.nms > 0:
+                keep_idx, keep_cnt = nms_batched(cand_boxes, cand_scores, seg_off, self.nms, -1, max(boxes_per_image))
+            else:  # "nms_thresh <= 0: no-op" (boxlist_ops.py:20-21): every candidate is kept
+                keep_cnt = seg_len
+                pos = torch.arange(cap, device=device, dtype=torch.int64)
+                seg_of = torch.searchsorted(seg_off[1:].long(), pos, right=True).clamp(max=n_seg - 1)
+                keep_idx = pos - seg_off.long()[seg_of]
+            det_boxes = torch.empty((cap, 4), dtype=torch.float32, device=device)
+            det_scores = torch.empty((cap,), dtype=torch.float32, device=device)
+            det_labels = torch.empty((cap,), dtype=torch.int64, device=device)
+            det_count = torch.empty((n_img,), dtype=torch.int32, device=device)
+            rc = lib.b200_select_detections(_ext.ptr(cand_boxes), _ext.ptr(cand_scores), _ext.ptr(seg_off),
+                                            _ext.ptr(keep_idx), _ext.ptr(keep_cnt), n_img, cfg,
+                                            int(self.detections_per_img), _ext.ptr(det_boxes), _ext.ptr(det_scores),
+                                            _ext.ptr(det_labels), _ext.ptr(det_count), st)
+            _ext.check(rc, "b200_select_detections")
+        bases = seg_off[torch.arange(n_img, device=device) * cfg]
+        host = torch.cat([det_count, bases, status]).tolist()        # the one host sync
+        counts, base, (total, overflow) = host[:n_img], host[n_img:2 * n_img], host[2 * n_img:]
+        if overflow:
+            raise RuntimeError("PostProcessor: %d candidates exceed the capacity %d (scores are not a softmax?)"
+                               % (total, cap))
+        results = []
+        for i in range(n_img):
+            o, n = base[i], counts[i]
+            bl = BoxList(det_boxes[o:o + n], image_shapes[i], mode="xyxy")
+            s = det_scores[o:o + n]
+            bl.add_field("scores", s)
+            bl.add_field("objectness", s)
+            bl.add_field("labels", det_labels[o:o + n])
+            results.append(bl)
+        return results
 
     def _filter_batched(self, proposals, class_prob, boxes_per_image, image_shapes, num_classes):
         """score > thresh, per-class NMS, top detections_per_img (reference :121-163), all

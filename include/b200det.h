@@ -235,6 +235,53 @@ int b200_colmax_decode(const uint64_t* col_best, int n_cols, int32_t* row_idx,
                        float* max_score, float* sigmoid_score, void* stream);
 
 /*
+ * Box-head candidates: decode + clip + score threshold + per-class compaction, all images and
+ * classes at once, feeding b200_nms_batched.  Replaces the front half of
+ * PostProcessor.forward / filter_results (modeling/roi_heads/box_head/inference.py:69-76, :96,
+ * :134-141): BoxCoder.decode (modeling/box_coder.py:52-95, legacy +1/-1, dw/dh clamped at
+ * log(1000/16)), BoxList.clip_to_image (structures/bounding_box.py:214-224), `scores > thresh`,
+ * and the per-class nonzero / gather.  The R x C x 4 decoded boxes are never materialised.
+ *
+ *   probs [n_rois, n_classes] fp32 (column 0 = background, skipped)
+ *   box_regression [n_rois, reg_stride] fp32; class_agnostic != 0: the LAST four columns are the
+ *       deltas of every class (inference.py:70), else columns 4j..4j+3 are class j's
+ *   boxes [n_rois, 4] fp32 xyxy proposals, 16-byte aligned; RoIs of image i are rows
+ *       roi_offsets[i] .. roi_offsets[i+1]-1 (int32 [n_images+1], device)
+ *   image_sizes [n_images, 2] fp32 (width, height), device;  wx..wh: BoxCoder weights
+ *   capacity: rows available in cand_*; with softmax scores at most
+ *       n_rois * min(n_classes-1, ceil(1/score_thresh)-1) candidates exist
+ * Outputs (segment s = image * (n_classes-1) + (class-1); inside a segment RoIs ascend -- the
+ * order the reference enumerates):
+ *   seg_len [n_segments] int32 scratch, seg_offsets [n_segments+1] int32
+ *   cand_boxes [capacity,4], cand_scores [capacity], cand_roi [capacity] int32 (row of the RoI)
+ *   status [2] int32: {total candidates, 1 if total > capacity (rows beyond capacity dropped)}
+ */
+int b200_box_candidates(const float* probs, const float* box_regression,
+                        const float* boxes, const int32_t* roi_offsets,
+                        const float* image_sizes, int n_images, int64_t n_rois,
+                        int n_classes, int reg_stride, int class_agnostic,
+                        float wx, float wy, float ww, float wh,
+                        float score_thresh, int64_t capacity, int32_t* seg_len,
+                        int32_t* seg_offsets, float* cand_boxes, float* cand_scores,
+                        int32_t* cand_roi, int32_t* status, void* stream);
+
+/*
+ * Detections per image after the per-class NMS.  Replaces the back half of filter_results
+ * (inference.py:143-163): concatenation of the classes' kept boxes (class ascending, NMS keep
+ * order inside a class) and, when more than detections_per_img are kept, the kthvalue rule
+ * `score >= (n - detections_per_img + 1)-th smallest score` (ties kept).
+ *   cand_*, seg_offsets: outputs of b200_box_candidates;  keep_idx / keep_cnt: outputs of
+ *   b200_nms_batched over the same segments;  classes_minus_1 <= 2048
+ *   det_boxes [capacity,4], det_scores [capacity], det_labels [capacity] int64: image i's
+ *   detections are rows seg_offsets[i*classes_minus_1] .. + det_count[i]
+ */
+int b200_select_detections(const float* cand_boxes, const float* cand_scores,
+                           const int32_t* seg_offsets, const int64_t* keep_idx,
+                           const int32_t* keep_cnt, int n_images, int classes_minus_1,
+                           int detections_per_img, float* det_boxes, float* det_scores,
+                           int64_t* det_labels, int32_t* det_count, void* stream);
+
+/*
  * RoIPool (max) forward / backward -- API compatibility with
  * _C.roi_pool_forward / _C.roi_pool_backward (csrc/ROIPool.h:11-48, kernels
  * csrc/cuda/ROIPool_cuda.cu:17-108).  NCHW only; no model in the reference uses it.

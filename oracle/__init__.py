@@ -225,6 +225,56 @@ def box_decode(codes, anchors, weights, img_size=None, clip=BBOX_XFORM_CLIP):
     return out
 
 
+def box_candidates(probs, box_regression, boxes, roi_offsets, image_sizes, weights, score_thresh,
+                   class_agnostic):
+    """Front half of PostProcessor.forward / filter_results for all images
+    (modeling/roi_heads/box_head/inference.py:69-76, :96, :134-141): decode + clip +
+    `scores > thresh`, candidates enumerated per (image, class 1..C-1) with RoIs ascending.
+    Returns (seg_offsets int32 [B*(C-1)+1], cand_boxes [N,4], cand_scores [N], cand_roi int32 [N])."""
+    probs, reg, boxes = _f32(probs), _f32(box_regression), _f32(boxes)
+    n_img, C = len(roi_offsets) - 1, probs.shape[1]
+    seg_off, cb, cs, cr = [0], [], [], []
+    for i in range(n_img):
+        r0, r1 = int(roi_offsets[i]), int(roi_offsets[i + 1])
+        w, h = image_sizes[i]
+        for j in range(1, C):
+            inds = np.nonzero(probs[r0:r1, j] > np.float32(score_thresh))[0] + r0          # :137
+            codes = reg[inds, -4:] if class_agnostic else reg[inds, 4 * j:4 * j + 4]          # :70, :139
+            cb.append(box_decode(codes, boxes[inds], weights, (float(w), float(h))))
+            cs.append(probs[inds, j])
+            cr.append(inds.astype(np.int32))
+            seg_off.append(seg_off[-1] + len(inds))
+    cat = lambda xs, shp, dt: np.concatenate(xs) if xs else np.zeros(shp, dt)
+    return (np.asarray(seg_off, np.int32), cat(cb, (0, 4), np.float32), cat(cs, (0,), np.float32),
+            cat(cr, (0,), np.int32))
+
+
+def select_detections(cand_boxes, cand_scores, seg_offsets, keep_idx, keep_cnt, n_images, detections_per_img):
+    """Back half of filter_results (inference.py:143-163): concatenate the classes' NMS results
+    (class ascending, keep order inside a class), then keep `score >= kthvalue(scores,
+    n - detections_per_img + 1)` when more than detections_per_img survive (ties kept).
+    Returns a list of (boxes, scores, labels int64) per image."""
+    cfg = (len(seg_offsets) - 1) // max(n_images, 1)
+    out = []
+    for i in range(n_images):
+        b, s, l = [], [], []
+        for j in range(cfg):
+            seg = i * cfg + j
+            o, k = int(seg_offsets[seg]), int(keep_cnt[seg])
+            idx = o + np.asarray(keep_idx[o:o + k], np.int64)
+            b.append(cand_boxes[idx]); s.append(cand_scores[idx]); l.append(np.full(k, j + 1, np.int64))
+        b = np.concatenate(b) if b else np.zeros((0, 4), np.float32)
+        s = np.concatenate(s) if s else np.zeros((0,), np.float32)
+        l = np.concatenate(l) if l else np.zeros((0,), np.int64)
+        n = len(s)
+        if n > detections_per_img > 0:
+            thr = np.sort(s, kind="stable")[n - detections_per_img]      # kthvalue(k = n - d + 1), 1-based
+            m = s >= thr
+            b, s, l = b[m], s[m], l[m]
+        out.append((b, s, l))
+    return out
+
+
 # --------------------------------------------------------------------------
 # Region -> class-embedding scoring (plain torch ops in the reference; numpy here)
 # --------------------------------------------------------------------------

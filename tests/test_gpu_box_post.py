@@ -1,0 +1,135 @@
+"""GPU parity of the box-head candidate / detection-selection kernels through the C ABI:
+b200_box_candidates and b200_select_detections against the numpy restatement of
+PostProcessor.filter_results, and the fused PostProcessor against its torch-op path.
+Integer outputs (segment offsets, RoI indices, labels, counts) bit-exact; scores bit-exact (copied);
+boxes within 1e-3 px (expf on the device vs libm in the oracle)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(seed, sizes, C, agnostic, quant=None):
+    rng = np.random.default_rng(seed)
+    R = sum(sizes)
+    logits = rng.standard_normal((R, C)).astype(np.float32) * 2.5
+    z = np.exp(logits - logits.max(1, keepdims=True))
+    probs = (z / z.sum(1, keepdims=True)).astype(np.float32)
+    if quant:  # coarse scores -> many exact ties for the kthvalue rule
+        probs = (np.round(probs * quant) / quant).astype(np.float32)
+    reg = (rng.standard_normal((R, 8 if agnostic else 4 * C)) * 0.5).astype(np.float32)
+    reg[::7, 2::4] = 9.0                                   # hits the log(1000/16) clamp
+    x1 = rng.uniform(-20, 600, R); y1 = rng.uniform(-20, 440, R)
+    boxes = np.stack([x1, y1, x1 + rng.uniform(1, 300, R), y1 + rng.uniform(1, 300, R)], 1).astype(np.float32)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    im = np.array([[640.0, 480.0]] * len(sizes), np.float32)
+    im[-1] = [333.0, 500.0]
+    return probs, reg, boxes, offs, im
+
+
+def _run_candidates(probs, reg, boxes, offs, im, thresh, agnostic, cap):
+    from cvpr22_cross_modal_pseudo_labeling_b200 import _ext
+    dev = torch.device("cuda")
+    t = lambda a: torch.from_numpy(a).to(dev)
+    p, r, b, o, s = t(probs), t(reg), t(boxes), t(offs), t(im)
+    n_img, C = len(offs) - 1, probs.shape[1]
+    n_seg = n_img * (C - 1)
+    seg_len = torch.empty(n_seg, dtype=torch.int32, device=dev)
+    seg_off = torch.empty(n_seg + 1, dtype=torch.int32, device=dev)
+    cb = torch.zeros((cap, 4), device=dev); cs = torch.zeros(cap, device=dev)
+    cr = torch.full((cap,), -1, dtype=torch.int32, device=dev)
+    status = torch.empty(2, dtype=torch.int32, device=dev)
+    rc = _ext.lib().b200_box_candidates(_ext.ptr(p), _ext.ptr(r), _ext.ptr(b), _ext.ptr(o), _ext.ptr(s), n_img,
+                                        probs.shape[0], C, reg.shape[1], int(agnostic), 10.0, 10.0, 5.0, 5.0,
+                                        thresh, cap, _ext.ptr(seg_len), _ext.ptr(seg_off), _ext.ptr(cb), _ext.ptr(cs),
+                                        _ext.ptr(cr), _ext.ptr(status), _ext.stream_ptr(dev))
+    _ext.check(rc, "b200_box_candidates")
+    return seg_off, cb, cs, cr, status
+
+
+@pytest.mark.parametrize("agnostic", [True, False])
+@pytest.mark.parametrize("sizes,C", [((300, 0, 157, 1), 21), ((64,), 2), ((1000, 1000), 66)])
+def test_box_candidates_match_oracle(agnostic, sizes, C):
+    probs, reg, boxes, offs, im = _inputs(11 + C, sizes, C, agnostic)
+    want_off, want_b, want_s, want_r = oracle.box_candidates(probs, reg, boxes, offs, im, (10., 10., 5., 5.), 0.05, agnostic)
+    cap = sum(sizes) * min(C - 1, 19)
+    seg_off, cb, cs, cr, status = _run_candidates(probs, reg, boxes, offs, im, 0.05, agnostic, cap)
+    n = int(want_off[-1])
+    assert status.tolist() == [n, 0]
+    assert np.array_equal(seg_off.cpu().numpy(), want_off)
+    assert np.array_equal(cr[:n].cpu().numpy(), want_r)
+    assert np.array_equal(cs[:n].cpu().numpy(), want_s)
+    np.testing.assert_allclose(cb[:n].cpu().numpy(), want_b, atol=1e-3)
+    assert n > 0 and float(cb[:n].min()) >= 0.0
+
+
+def test_box_candidates_capacity_overflow_is_reported():
+    probs, reg, boxes, offs, im = _inputs(5, (200,), 11, True)
+    want_off, *_ = oracle.box_candidates(probs, reg, boxes, offs, im, (10., 10., 5., 5.), 0.05, True)
+    seg_off, cb, cs, cr, status = _run_candidates(probs, reg, boxes, offs, im, 0.05, True, 16)
+    assert status.tolist() == [int(want_off[-1]), 1]          # total reported, nothing written past capacity
+    assert np.array_equal(seg_off.cpu().numpy(), want_off)
+
+
+@pytest.mark.parametrize("max_det", [100, 7, 0])
+def test_select_detections_matches_oracle(max_det):
+    from cvpr22_cross_modal_pseudo_labeling_b200 import _ext
+    from cvpr22_cross_modal_pseudo_labeling_b200.layers import nms_batched
+    sizes, C = (400, 3, 250), 31
+    probs, reg, boxes, offs, im = _inputs(77, sizes, C, True, quant=64)    # quantised scores: exact ties
+    cap = sum(sizes) * 19
+    seg_off, cb, cs, cr, status = _run_candidates(probs, reg, boxes, offs, im, 0.05, True, cap)
+    keep_idx, keep_cnt = nms_batched(cb, cs, seg_off, 0.5, -1, max(sizes))
+    dev = cb.device
+    db = torch.empty((cap, 4), device=dev); ds = torch.empty(cap, device=dev)
+    dl = torch.empty(cap, dtype=torch.int64, device=dev); dc = torch.empty(len(sizes), dtype=torch.int32, device=dev)
+    rc = _ext.lib().b200_select_detections(_ext.ptr(cb), _ext.ptr(cs), _ext.ptr(seg_off), _ext.ptr(keep_idx),
+                                           _ext.ptr(keep_cnt), len(sizes), C - 1, max_det, _ext.ptr(db), _ext.ptr(ds),
+                                           _ext.ptr(dl), _ext.ptr(dc), _ext.stream_ptr(dev))
+    _ext.check(rc, "b200_select_detections")
+    so = seg_off.cpu().numpy()
+    want = oracle.select_detections(cb.cpu().numpy(), cs.cpu().numpy(), so, keep_idx.cpu().numpy(),
+                                    keep_cnt.cpu().numpy(), len(sizes), max_det)
+    ties_seen = False
+    for i, (wb, ws, wl) in enumerate(want):
+        o, n = int(so[i * (C - 1)]), int(dc[i])
+        assert n == len(ws), (i, n, len(ws))
+        assert np.array_equal(ds[o:o + n].cpu().numpy(), ws)
+        assert np.array_equal(dl[o:o + n].cpu().numpy(), wl)
+        assert np.array_equal(db[o:o + n].cpu().numpy(), wb)
+        ties_seen |= max_det > 0 and n > max_det
+    if max_det == 7:
+        assert ties_seen                                       # the tie rule was exercised (more than 7 kept)
+
+
+@pytest.mark.parametrize("agnostic", [True, False])
+@pytest.mark.parametrize("max_det", [100, 5])
+def test_postprocessor_fused_equals_torch_path(agnostic, max_det):
+    """The library path and the torch-op path of PostProcessor produce the same detections
+    (labels / scores identical, boxes within 1e-3 px), incl. an empty image and ragged sizes."""
+    from cvpr22_cross_modal_pseudo_labeling_b200.modeling import BoxCoder, PostProcessor
+    from cvpr22_cross_modal_pseudo_labeling_b200.structures import BoxList
+    sizes, C = (180, 0, 75), 17
+    probs, reg, boxes, offs, im = _inputs(3, sizes, C, agnostic, quant=128 if max_det == 5 else None)
+    logits = torch.from_numpy(np.log(np.maximum(probs, 1e-12))).cuda()
+    logits.b200_probs = torch.from_numpy(probs).cuda()
+    regt = torch.from_numpy(reg).cuda()
+
+    def boxlists():
+        return [BoxList(torch.from_numpy(boxes[offs[i]:offs[i + 1]]).cuda(), (int(im[i, 0]), int(im[i, 1])))
+                for i in range(len(sizes))]
+    pp = PostProcessor(0.05, 0.5, max_det, BoxCoder((10., 10., 5., 5.)), cls_agnostic_bbox_reg=agnostic)
+    fused = pp((logits, regt), boxlists())
+    pp._fused_ok = lambda *a, **k: False                       # force the torch-op path
+    plain = pp((logits, regt), boxlists())
+    assert sum(len(b) for b in fused) > 0
+    for f, p in zip(fused, plain):
+        assert len(f) == len(p) and f.size == p.size
+        assert torch.equal(f.get_field("labels"), p.get_field("labels"))
+        assert torch.equal(f.get_field("scores"), p.get_field("scores"))
+        assert torch.allclose(f.bbox, p.bbox, atol=1e-3)
