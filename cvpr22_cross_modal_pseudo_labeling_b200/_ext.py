@@ -24,6 +24,12 @@ class b200_level(ctypes.Structure):
                 ("width", ctypes.c_int32), ("spatial_scale", ctypes.c_float)]
 
 
+class b200_rpn_level(ctypes.Structure):
+    _fields_ = [("objectness", ctypes.c_void_p), ("box_regression", ctypes.c_void_p), ("anchors", ctypes.c_void_p),
+                ("num_anchors", ctypes.c_int32), ("height", ctypes.c_int32), ("width", ctypes.c_int32),
+                ("anchors_per_image", ctypes.c_int32)]
+
+
 _lib = None
 
 _vp, _i, _i64, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t
@@ -40,6 +46,7 @@ SIGNATURES = {
     "b200_nhwc_to_nchw": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "b200_nms_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "b200_nms_batched": (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _f, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "b200_rpn_candidates": (_i, [ctypes.POINTER(b200_rpn_level), _i, _i, _vp, _i, _f, _f, _f, _f, _vp, _vp, _vp]),
     "b200_box_candidates": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _f, _f, _f, _f, _f, _i64,
                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200_select_detections": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
@@ -70,6 +77,9 @@ def lib():
         if hasattr(l, "b200_debug_bwd"):
             l.b200_debug_bwd.restype = None
             l.b200_debug_bwd.argtypes = [_i]
+        if hasattr(l, "b200_debug_rpn"):
+            l.b200_debug_rpn.restype = None
+            l.b200_debug_rpn.argtypes = [_i]
         if hasattr(l, "b200_debug_nms"):
             l.b200_debug_nms.restype = None
             l.b200_debug_nms.argtypes = [_i]
@@ -98,6 +108,11 @@ def ptr(t):
 
 def stream_ptr(device=None):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def debug_rpn(force_exact=False):
+    """Test hook: make b200_rpn_candidates skip the sampled lower bound and run the exact bisection."""
+    lib().b200_debug_rpn(int(force_exact))
 
 
 def debug_set(force_generic=False, exact=True, variant=0):

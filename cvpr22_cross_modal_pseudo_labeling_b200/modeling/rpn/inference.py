@@ -2,8 +2,11 @@
 modeling/rpn/inference.py:13-206) with ONE batched NMS launch for all (image, level) pairs
 instead of B x L calls of boxlist_nms (reference :111-122), and one host sync per forward.
 """
+import math
+
 import torch
 
+from ... import _ext
 from ...layers import nms_batched, select_topk
 from ...structures import BoxList, cat_boxlist
 from ..box_coder import BoxCoder
@@ -77,6 +80,44 @@ class RPNPostProcessor(torch.nn.Module):
         props = torch.min(props.clamp(min=0), lim)
         return props, obj
 
+    def _front_fused_ok(self, objectness, box_regression):
+        clip = getattr(self.box_coder, "bbox_xform_clip", math.log(1000. / 16))
+        return (all(o.is_cuda and o.dtype == torch.float32 for o in objectness) and
+                all(b.is_cuda and b.dtype == torch.float32 for b in box_regression) and
+                len(objectness) <= _ext.B200_MAX_LEVELS and abs(clip - math.log(1000. / 16)) < 1e-9 and
+                min(self.pre_nms_top_n, max(o[0].numel() for o in objectness)) <= 16384)
+
+    def _decode_all_fused(self, per_level, objectness, box_regression, sizes):
+        """All levels, all images: sigmoid + top-k + gather + decode + clip in ONE launch
+        (b200_rpn_candidates; reference :76-110).  Returns boxes [N*K, 4], scores [N*K] in the
+        (image, level) segment layout, and the per-level k."""
+        n_img = objectness[0].shape[0]
+        device = objectness[0].device
+        arr = (_ext.b200_rpn_level * len(objectness))()
+        hold, ks = [], []
+        for l, (a, o, b) in enumerate(zip(per_level, objectness, box_regression)):
+            N, A, H, W = o.shape
+            o, b = o.contiguous(), b.contiguous()
+            shared = all(x.bbox.data_ptr() == a[0].bbox.data_ptr() for x in a)
+            anc = a[0].bbox if shared else torch.cat([x.bbox for x in a], dim=0)
+            anc = anc.to(torch.float32).contiguous()
+            hold += [o, b, anc]
+            arr[l].objectness, arr[l].box_regression, arr[l].anchors = o.data_ptr(), b.data_ptr(), anc.data_ptr()
+            arr[l].num_anchors, arr[l].height, arr[l].width = A, H, W
+            arr[l].anchors_per_image = 0 if shared else 1
+            ks.append(min(self.pre_nms_top_n, A * H * W))
+        K = sum(ks)
+        im = torch.tensor([[float(s[0]), float(s[1])] for s in sizes], dtype=torch.float32).to(device)
+        boxes = torch.empty((n_img * K, 4), dtype=torch.float32, device=device)
+        score = torch.empty((n_img * K,), dtype=torch.float32, device=device)
+        wx, wy, ww, wh = [float(v) for v in self.box_coder.weights]
+        with torch.cuda.device(device):
+            rc = _ext.lib().b200_rpn_candidates(arr, len(objectness), n_img, _ext.ptr(im), int(self.pre_nms_top_n),
+                                                wx, wy, ww, wh, _ext.ptr(boxes), _ext.ptr(score),
+                                                _ext.stream_ptr(device))
+        _ext.check(rc, "b200_rpn_candidates")
+        return boxes, score, ks
+
     def forward(self, anchors, objectness, box_regression, targets=None):
         """anchors: list[image] of list[level] BoxList; objectness / box_regression:
         list[level] of [N, A, H, W] / [N, 4A, H, W].  Returns list[image] BoxList with
@@ -86,15 +127,19 @@ class RPNPostProcessor(torch.nn.Module):
         device = objectness[0].device
         per_level = list(zip(*anchors))
         sizes = [a[0].size for a in anchors]
-        props, scores = [], []
-        for a, o, b in zip(per_level, objectness, box_regression):
-            p, s = self._decode_level(a, o, b)
-            props.append(p)
-            scores.append(s)
-        ks = [p.shape[1] for p in props]
-        K = sum(ks)
-        boxes = torch.cat(props, dim=1).reshape(n_img * K, 4).contiguous()
-        score = torch.cat(scores, dim=1).reshape(n_img * K).contiguous()
+        if self._front_fused_ok(objectness, box_regression):
+            boxes, score, ks = self._decode_all_fused(per_level, objectness, box_regression, sizes)
+            K = sum(ks)
+        else:
+            props, scores = [], []
+            for a, o, b in zip(per_level, objectness, box_regression):
+                p, s = self._decode_level(a, o, b)
+                props.append(p)
+                scores.append(s)
+            ks = [p.shape[1] for p in props]
+            K = sum(ks)
+            boxes = torch.cat(props, dim=1).reshape(n_img * K, 4).contiguous()
+            score = torch.cat(scores, dim=1).reshape(n_img * K).contiguous()
         seg_off, seg_id, slot_start = self._segments(n_img, ks, device)
 
         if self.min_size > 0:

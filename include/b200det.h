@@ -235,6 +235,33 @@ int b200_colmax_decode(const uint64_t* col_best, int n_cols, int32_t* row_idx,
                        float* max_score, float* sigmoid_score, void* stream);
 
 /*
+ * RPN candidates: the per-level front end of the RPN post-processor, all (image, level) pairs in
+ * one launch.  Replaces RPNPostProcessor.forward_for_single_feature_map up to the
+ * NMS (modeling/rpn/inference.py:76-110): permute_and_flatten (modeling/rpn/utils.py:10-14),
+ * sigmoid, topk(min(pre_nms_top_n, A*H*W), sorted), gather of regression and anchors,
+ * BoxCoder.decode (modeling/box_coder.py:52-95), clip_to_image(remove_empty=False)
+ * (structures/bounding_box.py:214-219).
+ *   levels[n_levels] host array; anchors in the reference's flattened order (h*W + w)*A + a
+ *   image_sizes [n_images, 2] fp32 (width, height), device;  wx..wh: BoxCoder weights
+ * Outputs, K = sum_l min(pre_nms_top_n, A_l*H_l*W_l) slots per image, image-major, levels in
+ * order, descending objectness inside each (image, level) run (equal logits: ascending
+ * flattened index) -- the segment layout b200_nms_batched / b200_select_topk take:
+ *   boxes [n_images*K, 4] fp32 xyxy clipped, scores [n_images*K] fp32 = sigmoid(logit)
+ */
+typedef struct {
+  const float* objectness;     /* [N, A, H, W] fp32 contiguous logits              */
+  const float* box_regression; /* [N, 4A, H, W] fp32 contiguous                    */
+  const float* anchors;        /* [A*H*W, 4] or [N, A*H*W, 4] xyxy, 16-byte aligned */
+  int32_t num_anchors;         /* A                                                */
+  int32_t height, width;
+  int32_t anchors_per_image;   /* 0: one anchor set shared by all images           */
+} b200_rpn_level;
+int b200_rpn_candidates(const b200_rpn_level* levels, int n_levels, int n_images,
+                        const float* image_sizes, int pre_nms_top_n, float wx,
+                        float wy, float ww, float wh, float* boxes, float* scores,
+                        void* stream);
+
+/*
  * Box-head candidates: decode + clip + score threshold + per-class compaction, all images and
  * classes at once, feeding b200_nms_batched.  Replaces the front half of
  * PostProcessor.forward / filter_results (modeling/roi_heads/box_head/inference.py:69-76, :96,
