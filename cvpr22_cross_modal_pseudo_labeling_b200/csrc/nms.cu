@@ -69,6 +69,29 @@ __device__ __forceinline__ uint32_t orderable_f(float f) {
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
+// Is box b (area_b, x centre / reach cb) suppressed by one of `count` kept boxes?  The three
+// lists sit in shared memory (32-bit addresses: float2 centre/reach, float4 box, float area).
+// Warp-uniform trip count; a kept box out of x reach of all 32 lanes costs one 64-bit load, three
+// float instructions and a vote, the IoU test runs only when some lane is near.
+__device__ __forceinline__ bool survives_list(uint32_t c_a, uint32_t b_a, uint32_t a_a, int count, bool alive,
+                                              const float4 b, float area_b, const float2 cb, float thresh) {
+  for (int r = 0; r < count; ++r, c_a += 8, b_a += 16, a_a += 4) {
+    float cx, cr;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(cx), "=f"(cr) : "r"(c_a));
+    const bool near = alive && fabsf(cx - cb.x) - cr <= cb.y;
+    if (__any_sync(0xffffffffu, near)) {
+      if (near) {
+        float4 k;
+        float ak;
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(k.x), "=f"(k.y), "=f"(k.z), "=f"(k.w) : "r"(b_a));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(ak) : "r"(a_a));
+        if (suppresses(k, ak, b, area_b, thresh)) alive = false;
+      }
+    }
+  }
+  return alive;
+}
+
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kSortThreads)
 nms_sort_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores,
@@ -405,13 +428,7 @@ nms_fused_kernel(const float4* __restrict__ boxes, const float* __restrict__ sco
           const float4 b = sb[p];
           const float area_b = legacy_area(b);
           const float2 cb = x_reach(b, thresh);
-          for (int r = 0; r < nk; ++r) {  // warp-uniform trip count
-            const float2 c = klc[r];
-            const bool near = alive && fabsf(c.x - cb.x) - c.y <= cb.y;
-            if (__any_sync(0xffffffffu, near)) {
-              if (near && suppresses(kl[r], kla[r], b, area_b, thresh)) alive = false;
-            }
-          }
+          alive = survives_list(b200::smem_u32(klc), b200::smem_u32(kl), b200::smem_u32(kla), nk, alive, b, area_b, cb, thresh);
           if (alive0 && !alive) atomicOr(&remv[p >> 5], 1u << (p & 31));
         }
         __syncthreads();
@@ -509,13 +526,7 @@ nms_fused_kernel(const float4* __restrict__ boxes, const float* __restrict__ sco
           const float4 b = sb[p];
           const float area_b = legacy_area(b);
           const float2 cb = x_reach(b, thresh);
-          for (int r = 0; r < m; ++r) {  // warp-uniform trip count
-            const float2 c = kbc[r];
-            const bool near = alive && fabsf(c.x - cb.x) - c.y <= cb.y;
-            if (__any_sync(0xffffffffu, near)) {
-              if (near && suppresses(kb[r], ka[r], b, area_b, thresh)) alive = false;
-            }
-          }
+          alive = survives_list(b200::smem_u32(kbc), b200::smem_u32(kb), b200::smem_u32(ka), m, alive, b, area_b, cb, thresh);
           if (cand && !alive) atomicOr(&remv[p >> 5], 1u << (p & 31));
         }
       } else
