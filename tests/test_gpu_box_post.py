@@ -133,3 +133,29 @@ def test_postprocessor_fused_equals_torch_path(agnostic, max_det):
         assert torch.equal(f.get_field("labels"), p.get_field("labels"))
         assert torch.equal(f.get_field("scores"), p.get_field("scores"))
         assert torch.allclose(f.bbox, p.bbox, atol=1e-3)
+
+
+@pytest.mark.parametrize("nms,thresh", [(0.0, 0.05), (0.5, 0.0), (-1.0, 0.2)])
+def test_postprocessor_fused_degenerate_thresholds(nms, thresh):
+    """nms_thresh <= 0 is a no-op NMS (boxlist_ops.py:20-21) and score_thresh <= 0 admits every
+    (RoI, class) pair: the fused path must agree with the torch-op path there too."""
+    from cvpr22_cross_modal_pseudo_labeling_b200.modeling import BoxCoder, PostProcessor
+    from cvpr22_cross_modal_pseudo_labeling_b200.structures import BoxList
+    sizes, C = (40, 25), 6
+    probs, reg, boxes, offs, im = _inputs(9, sizes, C, True)
+    logits = torch.from_numpy(np.log(np.maximum(probs, 1e-12))).cuda()
+    logits.b200_probs = torch.from_numpy(probs).cuda()
+    regt = torch.from_numpy(reg).cuda()
+
+    def boxlists():
+        return [BoxList(torch.from_numpy(boxes[offs[i]:offs[i + 1]]).cuda(), (int(im[i, 0]), int(im[i, 1])))
+                for i in range(len(sizes))]
+    pp = PostProcessor(thresh, nms, 30, BoxCoder((10., 10., 5., 5.)), cls_agnostic_bbox_reg=True)
+    fused = pp((logits, regt), boxlists())
+    pp._fused_ok = lambda *a, **k: False
+    plain = pp((logits, regt), boxlists())
+    for f, p in zip(fused, plain):
+        assert len(f) == len(p) > 0
+        assert torch.equal(f.get_field("labels"), p.get_field("labels"))
+        assert torch.equal(f.get_field("scores"), p.get_field("scores"))
+        assert torch.allclose(f.bbox, p.bbox, atol=1e-3)
