@@ -39,6 +39,7 @@ struct MatchParams {
   int b_rows;    // rows of the E tile in shared memory (NP, or 512 when two boxes are loaded)
   int stages;
   int tmem_cols;
+  int ld;        // row pitch (floats) of the probs / logits outputs (>= N; column blocks of a wider matrix)
   int mode;
   float score_thresh;
   float* probs;
@@ -242,7 +243,7 @@ embed_match_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #pragma unroll 4
             for (int rr = 0; rr < 32; rr += 2) {
               const long long orow = row0 + quad * 32 + rr + rsub;
-              if (orow < p.M && c < N) outp[orow * N + c] = tile[(rr + rsub) * 17 + csub];
+              if (orow < p.M && c < N) outp[orow * p.ld + c] = tile[(rr + rsub) * 17 + csub];
             }
             __syncwarp();
           }
@@ -265,7 +266,7 @@ embed_match_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         for (int i = 0; i < 16; ++i) {
           const int c = c0 + i;
           if (c >= N) break;
-          if (p.logits && row_ok) p.logits[row * N + c] = v[i];
+          if (p.logits && row_ok) p.logits[row * p.ld + c] = v[i];
           const int cs = p.col_seg[c];
           if (cs < seg_lo || cs > seg_hi) continue;  // warp-uniform: no row of this warp can match
           unsigned long long key = 0;
@@ -349,11 +350,101 @@ int make_map(CUtensorMap* map, const void* base, long long rows, int K, int box_
 }  // namespace
 }  // namespace b200
 
+namespace b200 {
+namespace {
+
+// Row softmax over already computed logits [M, N] (row pitch N): what the fused epilogue does for
+// N <= 512, as a second pass for wider class matrices (b200_embed_match_wide).  One warp per row;
+// same arithmetic as the epilogue (__expf, first maximum wins ties).
+__global__ void __launch_bounds__(256) row_softmax_kernel(const float* __restrict__ logits, long long M, int N,
+                                                          float score_thresh, float* __restrict__ probs,
+                                                          int32_t* __restrict__ top_label,
+                                                          float* __restrict__ top_prob) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const float* x = logits + row * N;
+  float mx = -INFINITY, best = -INFINITY;
+  int best_c = 0x7fffffff;
+  for (int c = lane; c < N; c += 32) {
+    const float v = x[c];
+    mx = fmaxf(mx, v);
+    if (c >= 1 && v > best) {
+      best = v;
+      best_c = c;
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    const float ob = __shfl_xor_sync(0xffffffffu, best, d);
+    const int oc = __shfl_xor_sync(0xffffffffu, best_c, d);
+    if (ob > best || (ob == best && oc < best_c)) {
+      best = ob;
+      best_c = oc;
+    }
+  }
+  float sum = 0.f;
+  for (int c = lane; c < N; c += 32) sum += __expf(x[c] - mx);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+  const float inv = 1.0f / sum;
+  if (probs)
+    for (int c = lane; c < N; c += 32) probs[row * N + c] = __expf(x[c] - mx) * inv;
+  if (lane == 0 && top_label) {
+    const float bp = N > 1 ? __expf(best - mx) * inv : 0.f;
+    top_label[row] = (N > 1 && bp > score_thresh) ? best_c : 0;
+    if (top_prob) top_prob[row] = bp;
+  }
+}
+
+int embed_match_launch(const void* A_bf16, const void* E_bf16, int64_t n_rows, int n_cols, int dim, int ld, int mode,
+                       float score_thresh, float* probs, float* logits, int32_t* top_label, float* top_prob,
+                       const int32_t* row_seg, const int32_t* col_seg, const int32_t* row_seg_start,
+                       uint64_t* col_best, void* stream);
+
+}  // namespace
+}  // namespace b200
+
 extern "C" int b200_embed_match(const void* A_bf16, const void* E_bf16, int64_t n_rows, int n_cols, int dim,
                                 int mode, float score_thresh, float* probs, float* logits, int32_t* top_label,
                                 float* top_prob, const int32_t* row_seg, const int32_t* col_seg,
                                 const int32_t* row_seg_start, uint64_t* col_best, void* stream) {
+  return b200::embed_match_launch(A_bf16, E_bf16, n_rows, n_cols, dim, n_cols, mode, score_thresh, probs, logits,
+                                  top_label, top_prob, row_seg, col_seg, row_seg_start, col_best, stream);
+}
+
+extern "C" int b200_embed_match_wide(const void* A_bf16, const void* E_bf16, int64_t n_rows, int n_cols, int dim,
+                                     float score_thresh, float* probs, float* logits, int32_t* top_label,
+                                     float* top_prob, void* stream) {
   using namespace b200;
+  B200_REQUIRE(n_rows >= 0 && n_cols >= 0 && dim > 0, "embed_match_wide: bad shape");
+  if (n_rows == 0 || n_cols == 0) return B200_OK;
+  B200_REQUIRE(logits, "embed_match_wide: the [n_rows, n_cols] logits buffer is required (output and scratch)");
+  B200_REQUIRE(A_bf16 && E_bf16 && dim % 8 == 0, "embed_match_wide: null operand or dim %% 8 != 0");
+  // logits by column blocks of <= 512 (one TMEM allocation each), written at the full row pitch
+  for (int c0 = 0; c0 < n_cols; c0 += 512) {
+    const int nb = n_cols - c0 < 512 ? n_cols - c0 : 512;
+    const char* eb = static_cast<const char*>(E_bf16) + (size_t)c0 * dim * 2;
+    int rc = embed_match_launch(A_bf16, eb, n_rows, nb, dim, n_cols, B200_MATCH_SOFTMAX, score_thresh, nullptr,
+                                logits + c0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
+    if (rc != B200_OK) return rc;
+  }
+  if (probs || top_label) {
+    const long long blocks = (n_rows + 7) / 8;
+    row_softmax_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        logits, n_rows, n_cols, score_thresh, probs, top_label, top_prob);
+    B200_CHECK_LAUNCH("row_softmax_kernel");
+  }
+  return B200_OK;
+}
+
+namespace b200 {
+namespace {
+int embed_match_launch(const void* A_bf16, const void* E_bf16, int64_t n_rows, int n_cols, int dim, int ld, int mode,
+                       float score_thresh, float* probs, float* logits, int32_t* top_label, float* top_prob,
+                       const int32_t* row_seg, const int32_t* col_seg, const int32_t* row_seg_start,
+                       uint64_t* col_best, void* stream) {
   B200_REQUIRE(mode == B200_MATCH_SOFTMAX || mode == B200_MATCH_COLMAX, "embed_match: bad mode %d", mode);
   B200_REQUIRE(n_rows >= 0 && n_cols >= 0 && dim > 0, "embed_match: bad shape");
   if (n_rows == 0 || n_cols == 0) return B200_OK;
@@ -377,6 +468,7 @@ extern "C" int b200_embed_match(const void* A_bf16, const void* E_bf16, int64_t 
   p.b_rows = p.n_halves == 2 ? 512 : p.NP;
   p.tmem_cols = 32;
   while (p.tmem_cols < p.NP) p.tmem_cols <<= 1;
+  p.ld = ld;
   p.mode = mode;
   p.score_thresh = score_thresh;
   p.probs = probs;
@@ -411,6 +503,8 @@ extern "C" int b200_embed_match(const void* A_bf16, const void* E_bf16, int64_t 
   B200_CHECK_LAUNCH("embed_match_kernel");
   return B200_OK;
 }
+}  // namespace
+}  // namespace b200
 
 extern "C" int b200_colmax_decode(const uint64_t* col_best, int n_cols, int32_t* row_idx, float* max_score,
                                   float* sigmoid_score, void* stream) {

@@ -21,7 +21,7 @@ def _bf16(t, name):
 
 
 def embed_match_softmax(A, E, score_thresh=0.05, want_probs=True, want_logits=False, want_top=True):
-    """A [R,D], E [C,D] (row 0 = background) -> dict with any of
+    """A [R,D], E [C,D] (row 0 = background; any C: wider than 512 runs by column blocks) -> dict with any of
     probs [R,C] fp32 (row softmax), logits [R,C] fp32, top_label [R] int32 (best class >= 1,
     0 if its probability <= score_thresh), top_prob [R] fp32."""
     A, E = _bf16(A, "A"), _bf16(E, "E")
@@ -29,15 +29,22 @@ def embed_match_softmax(A, E, score_thresh=0.05, want_probs=True, want_logits=Fa
     c = E.shape[0]
     if E.shape[1] != d:
         raise ValueError("A and E must share the embedding dimension")
-    if c > MAX_COLS:
-        raise ValueError("at most %d classes per call (got %d)" % (MAX_COLS, c))
     dev = A.device
     out = {}
+    wide = c > MAX_COLS   # column blocks + a row-softmax pass (b200_embed_match_wide); needs the logits buffer
     probs = torch.empty((r, c), dtype=torch.float32, device=dev) if want_probs else None
-    logits = torch.empty((r, c), dtype=torch.float32, device=dev) if want_logits else None
+    logits = torch.empty((r, c), dtype=torch.float32, device=dev) if (want_logits or wide) else None
     top_label = torch.empty((r,), dtype=torch.int32, device=dev) if want_top else None
     top_prob = torch.empty((r,), dtype=torch.float32, device=dev) if want_top else None
-    if r > 0 and c > 0:
+    if r > 0 and c > 0 and wide:
+        with torch.cuda.device(dev):
+            rc = _ext.lib().b200_embed_match_wide(_ext.ptr(A), _ext.ptr(E), r, c, d, float(score_thresh),
+                                                  _ext.ptr(probs), _ext.ptr(logits), _ext.ptr(top_label),
+                                                  _ext.ptr(top_prob), _ext.stream_ptr(dev))
+        _ext.check(rc, "b200_embed_match_wide")
+        if not want_logits:
+            logits = None
+    elif r > 0 and c > 0:
         with torch.cuda.device(dev):
             rc = _ext.lib().b200_embed_match(_ext.ptr(A), _ext.ptr(E), r, c, d, _ext.B200_MATCH_SOFTMAX,
                                              float(score_thresh), _ext.ptr(probs), _ext.ptr(logits),

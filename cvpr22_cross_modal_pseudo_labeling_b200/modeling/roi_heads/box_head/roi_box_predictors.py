@@ -73,8 +73,7 @@ class FastRCNNPredictor(nn.Module):
         if self.embedding_based:
             cls_emb = self.emb_pred(x)
             E = self._class_matrix()
-            if E.shape[0] > 512 or not cls_emb.is_cuda:
-                # wider than one TMEM allocation (e.g. the 1203-word LVIS vocabulary): library GEMM
+            if not cls_emb.is_cuda:
                 cls_logit = torch.einsum("pe,ce->pc", cls_emb, self.cls_score)
             elif torch.is_grad_enabled() and cls_emb.requires_grad:
                 cls_logit = embed_logits(cls_emb, E)

@@ -230,6 +230,17 @@ int b200_embed_match(const void* A_bf16, const void* E_bf16, int64_t n_rows,
                      float* top_prob, const int32_t* row_seg,
                      const int32_t* col_seg, const int32_t* row_seg_start,
                      uint64_t* col_best, void* stream);
+/*
+ * SOFTMAX scoring against a class matrix of ANY width (e.g. the 1203-word LVIS vocabulary the
+ * student scores caption images against, detector/st_generalized_rcnn.py:71-75,:191): logits are
+ * produced by column blocks of <= 512 on the tensor cores straight into the caller's
+ * [n_rows, n_cols] logits buffer (required: output and scratch), then one row-softmax pass fills
+ * probs / top_label / top_prob (each optional) with the semantics of b200_embed_match.
+ */
+int b200_embed_match_wide(const void* A_bf16, const void* E_bf16, int64_t n_rows,
+                          int n_cols, int dim, float score_thresh, float* probs,
+                          float* logits, int32_t* top_label, float* top_prob,
+                          void* stream);
 /* col_best -> (row index local to the image, max score, sigmoid(max score)) */
 int b200_colmax_decode(const uint64_t* col_best, int n_cols, int32_t* row_idx,
                        float* max_score, float* sigmoid_score, void* stream);

@@ -21,7 +21,10 @@ def _inputs(seed, r, c, d, scale=3.0):
 
 
 @pytest.mark.parametrize("shape", [(1000, 66, 768), (300, 49, 768), (4096, 501, 512), (130, 18, 768),
-                                   (257, 1, 64), (5, 2, 8), (1000, 257, 200), (128, 512, 1024)])
+                                   (257, 1, 64), (5, 2, 8), (1000, 257, 200), (128, 512, 1024),
+                                   # wider than one TMEM allocation: column blocks + row softmax
+                                   # (1203 = the LVIS vocabulary of the student)
+                                   (2048, 1203, 768), (300, 513, 64), (129, 1030, 256)])
 def test_softmax_mode(shape):
     from cvpr22_cross_modal_pseudo_labeling_b200.layers import embed_match_softmax
     r, c, d = shape
@@ -109,5 +112,5 @@ def test_bad_arguments():
         embed_match_softmax(torch.zeros((4, 8)), torch.zeros((2, 8)))          # CPU tensors
     with pytest.raises(ValueError):
         embed_match_softmax(torch.zeros((4, 12), device="cuda"), torch.zeros((2, 12), device="cuda"))  # dim % 8
-    with pytest.raises(ValueError):
-        embed_match_softmax(torch.zeros((4, 8), device="cuda"), torch.zeros((513, 8), device="cuda"))
+    out = embed_match_softmax(torch.zeros((4, 8), device="cuda"), torch.zeros((513, 8), device="cuda"))
+    assert torch.allclose(out["probs"], torch.full((4, 513), 1.0 / 513, device="cuda"))   # wide path, uniform
