@@ -667,6 +667,55 @@ select_topk_kernel(const float4* __restrict__ boxes, const float* __restrict__ s
     }
   }
   __syncthreads();
+  // The kept list of a segment that arrived sorted (the RPN's top-k output) is itself in key
+  // order: then no sort is needed -- an entry's global rank is its index in its own run plus,
+  // for every other run, the number of smaller keys (binary search; keys are unique), and the
+  // entry goes straight to its output row.
+  int unsorted = 0;
+  for (int l = 0; l < segs_per_image; ++l) {
+    const int base = s_base[l], cnt = min(s_base[l + 1], total) - base;
+    for (int j = tid; j + 1 < cnt; j += kSelectThreads) unsorted |= skeys[base + j] > skeys[base + j + 1];
+  }
+  const int n_out = min(total, top_n);
+  if (!__syncthreads_or(unsorted)) {
+    for (int l = 0; l < segs_per_image; ++l) {
+      const int base = s_base[l], cnt = min(s_base[l + 1], total) - base;
+      for (int j = tid; j < cnt; j += kSelectThreads) {
+        const u64 key = skeys[base + j];
+        int rank = j;
+        for (int o = 0; o < segs_per_image; ++o) {
+          if (o == l) continue;
+          int lo = s_base[o], hi = min(s_base[o + 1], total);  // first index in [lo, hi) with key' > key
+          const int lo0 = lo;
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (skeys[mid] < key) lo = mid + 1;
+            else hi = mid;
+          }
+          rank += lo - lo0;
+        }
+        if (rank < top_n) {
+          const int gi = (int)(uint32_t)key;
+          const float4 b = boxes[gi];
+          float* r = rois_out + ((size_t)img * top_n + rank) * 5;
+          r[0] = (float)img;
+          r[1] = b.x;
+          r[2] = b.y;
+          r[3] = b.z;
+          r[4] = b.w;
+          if (scores_out) scores_out[(size_t)img * top_n + rank] = scores[gi];
+        }
+      }
+    }
+    for (int i = n_out + tid; i < top_n; i += kSelectThreads) {
+      float* r = rois_out + ((size_t)img * top_n + i) * 5;
+      r[0] = (float)img;
+      r[1] = r[2] = r[3] = r[4] = 0.f;
+      if (scores_out) scores_out[(size_t)img * top_n + i] = 0.f;
+    }
+    if (tid == 0) count_out[img] = n_out;
+    return;
+  }
   for (int k = 2; k <= npad; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
       for (int t = tid; t < (npad >> 1); t += kSelectThreads) {
@@ -680,7 +729,6 @@ select_topk_kernel(const float4* __restrict__ boxes, const float* __restrict__ s
       __syncthreads();
     }
   }
-  const int n_out = min(total, top_n);
   for (int i = tid; i < top_n; i += kSelectThreads) {
     float* r = rois_out + ((size_t)img * top_n + i) * 5;
     if (i < n_out) {

@@ -134,8 +134,11 @@ def test_nms_full_size_properties():
     assert np.array_equal(ki[a:a + int(kc_h[s])].cpu().numpy(), want)
 
 
-def test_select_topk_matches_numpy():
-    """Per-image cross-level top-k after the batched NMS (reference rpn/inference.py:173-180)."""
+@pytest.mark.parametrize("sorted_input", [True, False])
+def test_select_topk_matches_numpy(sorted_input):
+    """Per-image cross-level top-k after the batched NMS (reference rpn/inference.py:173-180):
+    sorted segments take the rank-merge path, unsorted ones the shared-memory sort; scores are
+    quantised so that equal scores occur across levels (ties: ascending box index)."""
     from cvpr22_cross_modal_pseudo_labeling_b200.layers import nms_batched, select_topk
     rng = np.random.default_rng(21)
     n_img, lens = 3, [700, 300, 64, 5]
@@ -144,8 +147,9 @@ def test_select_topk_matches_numpy():
     bs, ss = [], []
     for L in all_lens:
         b, s = synth.make_nms_boxes(rng, L)
-        o = np.argsort(-s, kind="stable")
-        bs.append(b[o]); ss.append(s[o] * rng.uniform(0.5, 1.0))     # levels get different score ranges
+        s = (np.round(s * rng.uniform(0.5, 1.0) * 512) / 512).astype(np.float32)   # levels: different ranges, ties
+        o = np.argsort(-s, kind="stable") if sorted_input else rng.permutation(L)
+        bs.append(b[o]); ss.append(s[o])
     boxes, scores = np.concatenate(bs), np.concatenate(ss)
     tb, ts = torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda()
     to = torch.from_numpy(off.astype(np.int32)).cuda()
