@@ -19,7 +19,8 @@
 //       gathering straight from global memory with geometry evaluated on the fly.
 //
 // kExact=true reproduces the reference's arithmetic bit for bit (separately rounded
-// multiplies and adds in its order); kExact=false lets the 4-tap sum use FMAs.
+// multiplies and adds in its order).  kExact=false ("fast math") sends the marching shapes to
+// the separable kernel of roi_align_fwd_sep.cu and lets the generic gather contract FMAs.
 #include "roi_align_fwd.cuh"
 
 namespace b200 {
@@ -320,17 +321,21 @@ int launch_forward(const LevelTable& lt, int layout, int C, const float* rois, i
   const bool march_ok = !g_force_generic && layout == B200_LAYOUT_NHWC && sr == 2 && PH <= 16 && PW <= 16 &&
                         C % kChunk == 0 && (NB * kChunk) % 4 == 0;
   B200_REQUIRE(n_rois * ((C + 15) / 16) < (int64_t)1 << 31, "roi_align: too many RoIs for one launch");
-  if (march_ok && !kExact) return launch_forward_sep(lt, C, rois, n_rois, PH, PW, out, out_mean, out_levels, g_variant, st);
   if (march_ok) {
-    // g_variant (tuning hook): CTAs/SM = 6 (default) / 5 / 4 for 128 threads, 3 / 3 / 2 for 256.
-    // (2 channels per lane with twice the warps was measured 35-55 % slower: V stays 4.)
-    if (PH * (kChunk / 4) <= 128) {
-      if (g_variant == 1) return launch_march<kExact, 128, 5, 4>(lt, C, rois, n_rois, PH, PW, out, out_mean, out_levels, st);
-      if (g_variant == 2) return launch_march<kExact, 128, 4, 4>(lt, C, rois, n_rois, PH, PW, out, out_mean, out_levels, st);
-      return launch_march<kExact, 128, 6, 4>(lt, C, rois, n_rois, PH, PW, out, out_mean, out_levels, st);
+    if constexpr (!kExact) {
+      // fast math: the separable marching kernel (roi_align_fwd_sep.cu)
+      return launch_forward_sep(lt, C, rois, n_rois, PH, PW, out, out_mean, out_levels, g_variant, st);
+    } else {
+      // g_variant (tuning hook): CTAs/SM = 6 (default) / 5 / 4 for 128 threads, 3 / 3 / 2 for 256.
+      // (2 channels per lane with twice the warps was measured 35-55 % slower: V stays 4.)
+      if (PH * (kChunk / 4) <= 128) {
+        if (g_variant == 1) return launch_march<true, 128, 5, 4>(lt, C, rois, n_rois, PH, PW, out, out_mean, out_levels, st);
+        if (g_variant == 2) return launch_march<true, 128, 4, 4>(lt, C, rois, n_rois, PH, PW, out, out_mean, out_levels, st);
+        return launch_march<true, 128, 6, 4>(lt, C, rois, n_rois, PH, PW, out, out_mean, out_levels, st);
+      }
+      if (g_variant == 2) return launch_march<true, 256, 2, 4>(lt, C, rois, n_rois, PH, PW, out, out_mean, out_levels, st);
+      return launch_march<true, 256, 3, 4>(lt, C, rois, n_rois, PH, PW, out, out_mean, out_levels, st);
     }
-    if (g_variant == 2) return launch_march<kExact, 256, 2, 4>(lt, C, rois, n_rois, PH, PW, out, out_mean, out_levels, st);
-    return launch_march<kExact, 256, 3, 4>(lt, C, rois, n_rois, PH, PW, out, out_mean, out_levels, st);
   }
   // generic: pick channels per CTA so that a CTA has >= ~2k units of work
   int c_per_cta = C;
