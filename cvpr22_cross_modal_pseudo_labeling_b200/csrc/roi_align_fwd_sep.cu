@@ -105,8 +105,11 @@ roi_align_fwd_sep(const LevelTable lt, int C, const float* __restrict__ rois, in
   bool use[4] = {false, false, false, false};
   if (active) merge_tap_rows(ytab[2 * ph], ytab[2 * ph + 1], row, w, use);
   const float* img = lt.data[h.level] + (size_t)h.batch * H * W * C + 4 * q;
-  const uint32_t xs_a = smem_u32(xs), co_a = smem_u32(colofs);
-  const uint32_t tile_a = smem_u32(out_s) + 4u * (uint32_t)(tile_row(4 * q, NB, swz) + ph * PW);
+  uint32_t xs_a = smem_u32(xs), co_a = smem_u32(colofs);
+  uint32_t tile_a = smem_u32(out_s) + 4u * (uint32_t)(tile_row(4 * q, NB, swz) + ph * PW);
+  // opaque to the optimiser: otherwise ptxas re-derives these shared addresses (S2UR / UMOV /
+  // ULEA chains, ~25 % of the issued instructions) at every use instead of keeping 3 registers
+  asm volatile("" : "+r"(xs_a), "+r"(co_a), "+r"(tile_a));
   float4 raw[kDepth][4];  // kDepth columns in flight
 #pragma unroll
   for (int d = 0; d < kDepth; ++d)
