@@ -11,6 +11,7 @@ by the object of the same name from this package (same call signature):
   maskrcnn_benchmark/modeling/rpn/inference.py:13       RPNPostProcessor        (one batched NMS per forward)
   maskrcnn_benchmark/modeling/roi_heads/box_head/inference.py:12       PostProcessor
   maskrcnn_benchmark/modeling/roi_heads/box_head/roi_box_predictors.py:8   FastRCNNPredictor
+  maskrcnn_benchmark/modeling/roi_heads/mask_head/inference.py:11,168     MaskPostProcessor, Masker (one paste launch per image)
 
 Call it after `import maskrcnn_benchmark` and before `build_detection_model(cfg)`.
 """
@@ -22,6 +23,7 @@ def install(verbose=False):
     from . import layers, modeling, structures
     from .modeling.roi_heads.box_head import inference as box_inference
     from .modeling.roi_heads.box_head import roi_box_predictors
+    from .modeling.roi_heads.mask_head import inference as mask_inference
     from .modeling.rpn import inference as rpn_inference
 
     patches = {
@@ -43,6 +45,9 @@ def install(verbose=False):
         "maskrcnn_benchmark.modeling.roi_heads.box_head.roi_box_predictors": dict(
             FastRCNNPredictor=roi_box_predictors.FastRCNNPredictor,
             make_roi_box_predictor=roi_box_predictors.make_roi_box_predictor),
+        "maskrcnn_benchmark.modeling.roi_heads.mask_head.inference": dict(
+            MaskPostProcessor=mask_inference.MaskPostProcessor, Masker=mask_inference.Masker,
+            make_roi_mask_post_processor=mask_inference.make_roi_mask_post_processor),
     }
     done = []
     for mod_name, attrs in patches.items():

@@ -320,6 +320,19 @@ int b200_select_detections(const float* cand_boxes, const float* cand_scores,
                            int64_t* det_labels, int32_t* det_count, void* stream);
 
 /*
+ * Mask paste: Masker.forward_single_image / paste_mask_in_image for all boxes of an
+ * image in one launch (modeling/roi_heads/mask_head/inference.py:96-186): zero border of
+ * `padding` pixels around each M x M mask probability map, the box grown by the same factor and
+ * truncated to int32, bilinear resize to the box size (F.interpolate, align_corners=False),
+ * `> thresh`, paste into a zero image.
+ *   masks [n_boxes, M, M] fp32 probabilities;  boxes [n_boxes, 4] fp32 xyxy (image pixels)
+ *   out   [n_boxes, im_h, im_w] uint8 (torch.bool), every byte written (0 outside the boxes)
+ */
+int b200_paste_masks(const float* masks, const float* boxes, int64_t n_boxes,
+                     int mask_size, int padding, int im_h, int im_w, float thresh,
+                     uint8_t* out, void* stream);
+
+/*
  * RoIPool (max) forward / backward -- API compatibility with
  * _C.roi_pool_forward / _C.roi_pool_backward (csrc/ROIPool.h:11-48, kernels
  * csrc/cuda/ROIPool_cuda.cu:17-108).  NCHW only; no model in the reference uses it.

@@ -275,6 +275,46 @@ def select_detections(cand_boxes, cand_scores, seg_offsets, keep_idx, keep_cnt, 
     return out
 
 
+def paste_masks(masks, boxes, im_h, im_w, thresh=0.5, padding=1):
+    """Masker.forward_single_image (modeling/roi_heads/mask_head/inference.py:96-186) in numpy
+    float32: expand_masks / expand_boxes, int32 truncation, bilinear resize with the index and
+    weight rules of F.interpolate(align_corners=False) (at::native area_pixel_compute_source_index
+    + guard_index_and_lambda), `> thresh`, paste.  masks [N, M, M] -> bool [N, im_h, im_w]."""
+    f = np.float32
+    masks, boxes = _f32(masks), _f32(boxes)
+    N, M = masks.shape[0], masks.shape[-1]
+    Mp = M + 2 * padding
+    out = np.zeros((N, im_h, im_w), np.bool_)
+
+    def axis(scale, n_out, n_in):
+        s = scale * (np.arange(n_out, dtype=f) + f(0.5)) - f(0.5)
+        s = np.where(s < 0, f(0), s).astype(f)
+        i0 = np.minimum(np.floor(s).astype(np.int64), n_in - 1)
+        i1 = i0 + (i0 < n_in - 1)
+        l1 = np.clip(s - i0.astype(f), f(0), f(1)).astype(f)
+        return i0, i1, (f(1) - l1).astype(f), l1
+
+    for n in range(N):
+        pm = np.zeros((Mp, Mp), f)
+        pm[padding:Mp - padding, padding:Mp - padding] = masks[n].reshape(M, M)
+        scale = f(Mp) / f(M)
+        x1, y1, x2, y2 = boxes[n]
+        w_half, h_half = (x2 - x1) * f(0.5) * scale, (y2 - y1) * f(0.5) * scale
+        x_c, y_c = (x2 + x1) * f(0.5), (y2 + y1) * f(0.5)
+        b = [int(np.trunc(v)) for v in (x_c - w_half, y_c - h_half, x_c + w_half, y_c + h_half)]
+        w, h = max(b[2] - b[0] + 1, 1), max(b[3] - b[1] + 1, 1)
+        yi0, yi1, yl0, yl1 = axis(f(Mp) / f(h), h, Mp)
+        xi0, xi1, xl0, xl1 = axis(f(Mp) / f(w), w, Mp)
+        top = xl0[None] * pm[yi0][:, xi0] + xl1[None] * pm[yi0][:, xi1]
+        bot = xl0[None] * pm[yi1][:, xi0] + xl1[None] * pm[yi1][:, xi1]
+        m = (yl0[:, None] * top + yl1[:, None] * bot) > f(thresh)
+        x_0, x_1 = max(b[0], 0), min(b[2] + 1, im_w)
+        y_0, y_1 = max(b[1], 0), min(b[3] + 1, im_h)
+        if x_1 > x_0 and y_1 > y_0:
+            out[n, y_0:y_1, x_0:x_1] = m[y_0 - b[1]:y_1 - b[1], x_0 - b[0]:x_1 - b[0]]
+    return out
+
+
 # --------------------------------------------------------------------------
 # Region -> class-embedding scoring (plain torch ops in the reference; numpy here)
 # --------------------------------------------------------------------------

@@ -166,6 +166,42 @@ def gen_box_head(rng):
     return out
 
 
+def gen_masks(rng):
+    """The reference's MaskPostProcessor + Masker (mask_head/inference.py:11-66, :168-205) on two
+    images: boxes inside, straddling every border, tiny (sub-pixel) and one fully outside."""
+    from maskrcnn_benchmark.modeling.roi_heads.mask_head.inference import Masker, MaskPostProcessor
+    from maskrcnn_benchmark.structures.bounding_box import BoxList
+    out = {}
+    sizes = [(320, 200), (171, 243)]
+    boxes = [np.array([[10.3, 20.7, 80.2, 90.9], [-25.0, -13.5, 60.0, 40.0], [250.0, 150.0, 400.0, 260.0],
+                       [100.2, 50.9, 100.6, 51.3], [5.0, 3.0, 318.0, 198.0], [500.0, 500.0, 600.0, 650.0]], np.float32),
+             np.array([[0.0, 0.0, 170.0, 242.0], [33.3, 77.7, 44.4, 201.1], [160.5, 230.5, 175.0, 250.0],
+                       [60.0, 10.0, 61.0, 240.0]], np.float32)]
+    labels = [rng.integers(1, 5, len(b)) for b in boxes]
+    n = sum(len(b) for b in boxes)
+    x = (rng.standard_normal((n, 5, 14, 14)) * 2).astype(np.float32)
+    # smooth the logits a little so that masks have blobs, not salt and pepper
+    x = (x + np.roll(x, 1, 2) + np.roll(x, 1, 3) + np.roll(x, (1, 1), (2, 3))) / 2
+    bl = []
+    for b, lab, sz in zip(boxes, labels, sizes):
+        t = BoxList(torch.from_numpy(b), sz, mode="xyxy")
+        t.add_field("labels", torch.from_numpy(lab.astype(np.int64)))
+        bl.append(t)
+    res = MaskPostProcessor(masker=Masker(threshold=0.5, padding=1))(torch.from_numpy(x), bl)
+    out["mk_logits"] = x
+    for i, (b, lab, sz, r) in enumerate(zip(boxes, labels, sizes, res)):
+        out["mk_boxes%d" % i], out["mk_labels%d" % i], out["mk_size%d" % i] = b, lab.astype(np.int64), np.array(sz)
+        m = r.get_field("mask").numpy()
+        assert m.dtype == np.bool_ and m.shape == (len(b), 1, sz[1], sz[0])
+        out["mk_mask%d_packed" % i] = np.packbits(m.reshape(-1))
+        # pin the numpy restatement against the reference right here
+        prob = torch.from_numpy(x).sigmoid().numpy()
+        o = sum(len(bb) for bb in boxes[:i])
+        sel = prob[np.arange(o, o + len(b)), lab]
+        assert np.array_equal(oracle.paste_masks(sel, b, sz[1], sz[0], 0.5, 1), m[:, 0]), "oracle.paste_masks != reference"
+    return out
+
+
 def main():
     install_reference()
     rng = np.random.default_rng(20221017)
@@ -174,6 +210,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "pooler.npz"), **gen_pooler(rng))
     np.savez_compressed(os.path.join(HERE, "rpn.npz"), **gen_rpn(rng))
     np.savez_compressed(os.path.join(HERE, "box_head.npz"), **gen_box_head(rng))
+    np.savez_compressed(os.path.join(HERE, "masks.npz"), **gen_masks(np.random.default_rng(99)))
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KB")

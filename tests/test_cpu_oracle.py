@@ -129,3 +129,23 @@ def test_level_map_matches_torch():
     area = (b[:, 2] - b[:, 0] + 1) * (b[:, 3] - b[:, 1] + 1)
     t = torch.floor(4 + torch.log2(torch.sqrt(area) / 224 + 1e-6)).clamp(min=2.0, max=5.0).to(torch.int64) - 2
     assert int((t.numpy() != lv).sum()) == 0
+
+
+def test_paste_masks_oracle_matches_reference_golden():
+    """oracle.paste_masks == the reference's MaskPostProcessor + Masker outputs (tests/golden/masks.npz,
+    generated by tests/golden/make_golden.py from /root/reference)."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "masks.npz"))
+    prob = 1.0 / (1.0 + np.exp(-g["mk_logits"].astype(np.float64)))
+    o = 0
+    for i in range(2):
+        boxes, labels = g["mk_boxes%d" % i], g["mk_labels%d" % i]
+        w, h = [int(v) for v in g["mk_size%d" % i]]
+        n = len(boxes)
+        want = np.unpackbits(g["mk_mask%d_packed" % i])[:n * h * w].reshape(n, h, w).astype(bool)
+        # probabilities exactly as torch computes them are needed for bit parity at the threshold; the
+        # fp64 sigmoid rounds to the same fp32 value except in rare last-ulp cases: allow 1e-5 of the pixels
+        sel = prob[np.arange(o, o + n), labels].astype(np.float32)
+        got = oracle.paste_masks(sel, boxes, h, w, 0.5, 1)
+        assert (got != want).mean() <= 1e-5
+        assert got[-1 if i == 0 else 0].any() == want[-1 if i == 0 else 0].any()
+        o += n
