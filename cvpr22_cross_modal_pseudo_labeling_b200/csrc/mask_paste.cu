@@ -24,11 +24,12 @@ __device__ __forceinline__ void src_index(float scale, int dst, int in_size, int
 
 constexpr int kPasteThreads = 128;
 constexpr int kPxPerThread = 16;
+constexpr int kRowsPerCta = 8;  // amortises the box set-up over several image rows
 
 __global__ void __launch_bounds__(kPasteThreads)
 paste_masks_kernel(const float* __restrict__ masks, const float* __restrict__ boxes, int M, int padding, int im_h,
                    int im_w, int row_words, float thresh, uint8_t* __restrict__ out) {
-  const int n = blockIdx.y, y = blockIdx.x;
+  const int n = blockIdx.y;
   const float* bx = boxes + (size_t)n * 4;
   // expand_boxes (:96-111) with scale = (M + 2p) / M, then .to(int32): truncation toward zero
   const int Mp = M + 2 * padding;
@@ -40,20 +41,25 @@ paste_masks_kernel(const float* __restrict__ masks, const float* __restrict__ bo
   const int b1 = (int)__fsub_rn(y_c, h_half), b3 = (int)__fadd_rn(y_c, h_half);
   const int w = max(b2 - b0 + 1, 1), h = max(b3 - b1 + 1, 1);
   const int x_0 = max(b0, 0), x_1 = min(b2 + 1, im_w), y_0 = max(b1, 0), y_1 = min(b3 + 1, im_h);
-  const bool row_in = y >= y_0 && y < y_1;
-  int yi0 = 0, yi1 = 0;
-  float yl0 = 0.f, yl1 = 0.f;
-  if (row_in) src_index((float)Mp / (float)h, y - b1, Mp, yi0, yi1, yl0, yl1);
-  const float sx = (float)Mp / (float)w;
+  const float sx = (float)Mp / (float)w, sy = (float)Mp / (float)h;
   const float* mk = masks + (size_t)n * M * M;
   // padded mask value: zero border of `padding` pixels around the M x M mask
   auto at = [&](int py, int px) -> float {
     const int my = py - padding, mx = px - padding;
     return (my >= 0 && my < M && mx >= 0 && mx < M) ? __ldg(mk + my * M + mx) : 0.f;
   };
+  const int y_end = min((int)(blockIdx.x + 1) * kRowsPerCta, im_h);
+  for (int y = blockIdx.x * kRowsPerCta; y < y_end; ++y) {
+  const bool row_in = y >= y_0 && y < y_1;
+  int yi0 = 0, yi1 = 0;
+  float yl0 = 0.f, yl1 = 0.f;
+  if (row_in) src_index(sy, y - b1, Mp, yi0, yi1, yl0, yl1);
   uint8_t* orow = out + ((size_t)n * im_h + y) * im_w;
+  // 16-byte words are aligned to the ADDRESS, not to x = 0 (row pitch = im_w is arbitrary): the
+  // first and last word of a row may be partial, every other one is a single 128-bit store
+  const int mis = (int)(reinterpret_cast<uintptr_t>(orow) & 15);
   for (int wd = threadIdx.x; wd < row_words; wd += kPasteThreads) {
-    const int xb = wd * kPxPerThread;
+    const int xb = wd * kPxPerThread - mis;
     uint32_t packed[4] = {0u, 0u, 0u, 0u};
     if (row_in && xb < x_1 && xb + kPxPerThread > x_0) {
 #pragma unroll
@@ -71,11 +77,13 @@ paste_masks_kernel(const float* __restrict__ masks, const float* __restrict__ bo
         }
       }
     }
-    if (xb + kPxPerThread <= im_w && ((reinterpret_cast<uintptr_t>(orow + xb) & 15) == 0)) {
+    if (xb >= 0 && xb + kPxPerThread <= im_w) {
       *reinterpret_cast<uint4*>(orow + xb) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
     } else {
-      for (int k = 0; k < kPxPerThread && xb + k < im_w; ++k) orow[xb + k] = (uint8_t)((packed[k >> 2] >> (8 * (k & 3))) & 1u);
+      for (int k = 0; k < kPxPerThread; ++k)
+        if (xb + k >= 0 && xb + k < im_w) orow[xb + k] = (uint8_t)((packed[k >> 2] >> (8 * (k & 3))) & 1u);
     }
+  }
   }
 }
 
@@ -90,8 +98,8 @@ extern "C" int b200_paste_masks(const float* masks, const float* boxes, int64_t 
   if (n_boxes == 0) return B200_OK;
   B200_REQUIRE(masks && boxes && out, "paste_masks: null pointer");
   B200_REQUIRE(n_boxes <= 65535 && im_h <= 2147483647, "paste_masks: too many boxes for one launch");
-  const int row_words = (im_w + kPxPerThread - 1) / kPxPerThread;
-  paste_masks_kernel<<<dim3((unsigned)im_h, (unsigned)n_boxes), kPasteThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+  const int row_words = (im_w + kPxPerThread - 1) / kPxPerThread + 1;  // + 1: rows need not start 16-byte aligned
+  paste_masks_kernel<<<dim3((unsigned)((im_h + kRowsPerCta - 1) / kRowsPerCta), (unsigned)n_boxes), kPasteThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       masks, boxes, mask_size, padding, im_h, im_w, row_words, thresh, out);
   B200_CHECK_LAUNCH("paste_masks_kernel");
   return B200_OK;
