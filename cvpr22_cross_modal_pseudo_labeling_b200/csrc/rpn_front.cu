@@ -68,17 +68,74 @@ __device__ __forceinline__ int block_sum(int v, int* scratch) {
 
 constexpr int kRpnSample = 4096;
 
-// append `take`n entries of this pass position to the candidate list (warp-aggregated)
-__device__ __forceinline__ void append(bool take, u64 packed, u64* cand, int cap, int* counter) {
-  const int lane = threadIdx.x & 31;
-  const uint32_t tm = __ballot_sync(0xffffffffu, take);
-  int base = 0;
-  if (lane == 0 && tm) base = atomicAdd(counter, __popc(tm));
-  base = __shfl_sync(0xffffffffu, base, 0);
-  if (take) {
-    const int pos = base + __popc(tm & ((1u << lane) - 1));
-    if (pos < cap) cand[pos] = packed;
+// Ordered, atomic-free collection of the logits that satisfy `take(key, flat)` into cand[]:
+// pass A counts per warp, a scan over the 32 warp totals gives every warp its base, pass B
+// re-reads the (L2-resident) logits and writes.  A single shared counter with warp-aggregated
+// atomics serialised the 32 warps (6 k atomics on one address per level-2 CTA: 0.2 ms).
+// Returns the total; nothing is written when it exceeds `cap`.
+constexpr int kRpnUnroll = 8;  // logits fetched per thread before any is consumed (hides the L2 latency)
+
+template <class Take>
+__device__ __forceinline__ int collect(const float* __restrict__ obj, int M, int HW, int A, u64* cand, int cap,
+                                       int* scratch, Take take) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kStep = kRpnThreads * kRpnUnroll;
+  const int m_round = (M + kStep - 1) / kStep * kStep;
+  int c = 0;
+  for (int i0 = 0; i0 < m_round; i0 += kStep) {
+    float v[kRpnUnroll];
+#pragma unroll
+    for (int u = 0; u < kRpnUnroll; ++u) {
+      const int i = i0 + u * kRpnThreads + tid;
+      v[u] = i < M ? obj[i] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < kRpnUnroll; ++u) {
+      const int i = i0 + u * kRpnThreads + tid;
+      bool t = false;
+      if (i < M) {
+        const int a = i / HW, p = i - a * HW;
+        t = take(orderable_bits(v[u]), (uint32_t)(p * A + a));
+      }
+      c += __popc(__ballot_sync(0xffffffffu, t));
+    }
   }
+  __syncthreads();  // scratch free
+  if (lane == 0) scratch[warp] = c;
+  __syncthreads();
+  int w = lane < kRpnThreads / 32 ? scratch[lane] : 0, incl = w;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += o;
+  }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  int base = __shfl_sync(0xffffffffu, incl - w, warp);
+  if (total > cap) return total;
+  for (int i0 = 0; i0 < m_round; i0 += kStep) {
+    float v[kRpnUnroll];
+#pragma unroll
+    for (int u = 0; u < kRpnUnroll; ++u) {
+      const int i = i0 + u * kRpnThreads + tid;
+      v[u] = i < M ? obj[i] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < kRpnUnroll; ++u) {
+      const int i = i0 + u * kRpnThreads + tid;
+      bool t = false;
+      u64 pk = 0ull;
+      if (i < M) {
+        const int a = i / HW, p = i - a * HW;
+        const uint32_t key = orderable_bits(v[u]), flat = (uint32_t)(p * A + a);  // (h*W + w)*A + a
+        t = take(key, flat);
+        pk = ((u64)key << 32) | (u64)(0xffffffffu - flat);
+      }
+      const uint32_t tm = __ballot_sync(0xffffffffu, t);
+      if (t) cand[base + __popc(tm & ((1u << lane) - 1))] = pk;
+      base += __popc(tm);
+    }
+  }
+  return total;
 }
 
 __device__ __forceinline__ void bitonic_desc(u64* keys, int n) {  // n: power of two
@@ -103,30 +160,17 @@ rpn_front_kernel(const RpnLevels lv, const float* __restrict__ im_sizes, float w
   extern __shared__ __align__(16) unsigned char rpn_smem[];
   u64* cand = reinterpret_cast<u64*>(rpn_smem);  // [cap] (key << 32) | (0xffffffff - flattened index)
   __shared__ int scratch[32];
-  __shared__ int n_cand;
   const int l = blockIdx.x, n = blockIdx.y, tid = threadIdx.x;
   const int A = lv.A[l], HW = lv.HW[l], M = A * HW, k = lv.k[l];
   const float* obj = lv.obj[l] + (size_t)n * M;
-  const int m_round = (M + kRpnThreads - 1) / kRpnThreads * kRpnThreads;
-  auto packed_at = [&](int i, uint32_t key) {  // i: memory position a*HW + p
-    const int a = i / HW, p = i - a * HW;
-    return ((u64)key << 32) | (u64)(0xffffffffu - (uint32_t)(p * A + a));  // (h*W + w)*A + a
-  };
 
   // ---- 1. candidates ----------------------------------------------------------------------
-  bool have = false;
-  if (tid == 0) n_cand = 0;
-  __syncthreads();
+  int nc = -1;  // entries in cand[] (uniform); -1: not collected yet
   if (M <= cap) {  // small level: everything is a candidate
-    for (int i0 = 0; i0 < m_round; i0 += kRpnThreads) {
-      const int i = i0 + tid;
-      const uint32_t key = i < M ? orderable_bits(obj[i]) : 0u;
-      append(i < M, i < M ? packed_at(i, key) : 0ull, cand, cap, &n_cand);
-    }
-    have = true;
+    nc = collect(obj, M, HW, A, cand, cap, scratch, [](uint32_t, uint32_t) { return true; });
   } else if (!force_exact) {
     // sample -> lower bound that should leave ~ (k + cap) / 2 elements above it
-    u64* sk = cand + kRpnSample;  // sort the samples as u64 in the upper part of the buffer (cap >= 8192)
+    u64* sk = cand + kRpnSample;  // sort the samples in the upper part of the buffer (cap >= 8192)
     for (int t = tid; t < kRpnSample; t += kRpnThreads)
       sk[t] = orderable_bits(obj[(int)(((long long)t * M) / kRpnSample)]);
     __syncthreads();
@@ -136,17 +180,10 @@ rpn_front_kernel(const RpnLevels lv, const float* __restrict__ im_sizes, float w
     if (q > kRpnSample - 1) q = kRpnSample - 1;
     const uint32_t lo0 = (uint32_t)sk[q];
     __syncthreads();
-    for (int i0 = 0; i0 < m_round; i0 += kRpnThreads) {
-      const int i = i0 + tid;
-      const uint32_t key = i < M ? orderable_bits(obj[i]) : 0u;
-      const bool take = i < M && key >= lo0;
-      append(take, take ? packed_at(i, key) : 0ull, cand, cap, &n_cand);
-    }
-    __syncthreads();
-    have = n_cand >= k && n_cand <= cap;  // uniform
-    __syncthreads();
+    nc = collect(obj, M, HW, A, cand, cap, scratch, [lo0](uint32_t key, uint32_t) { return key >= lo0; });
+    if (nc < k || nc > cap) nc = -1;  // uniform
   }
-  if (!have) {
+  if (nc < 0) {
     // exact fallback: k-th largest key by bisection (invariant: count(key >= lo) >= k)
     uint32_t lo = 0u, hi = 0xffffffffu;
     while (lo < hi) {
@@ -182,25 +219,45 @@ rpn_front_kernel(const RpnLevels lv, const float* __restrict__ im_sizes, float w
       }
       flat_max = flo;
     }
-    __syncthreads();
-    if (tid == 0) n_cand = 0;
-    __syncthreads();
-    for (int i0 = 0; i0 < m_round; i0 += kRpnThreads) {
-      const int i = i0 + tid;
-      uint32_t key = 0u;
-      bool take = false;
-      u64 pk = 0ull;
-      if (i < M) {
-        key = orderable_bits(obj[i]);
-        pk = packed_at(i, key);
-        take = key > thr || (key == thr && (0xffffffffu - (uint32_t)pk) <= flat_max);
-      }
-      append(take, pk, cand, cap, &n_cand);
-    }
+    nc = collect(obj, M, HW, A, cand, cap, scratch,
+                 [thr, flat_max](uint32_t key, uint32_t flat) { return key > thr || (key == thr && flat <= flat_max); });
   }
   __syncthreads();
-  // ---- 2. sort: the first k entries are the result --------------------------------------
-  const int nc = n_cand;
+  // ---- 2. trim the list to exactly k entries, then sort them ------------------------------
+  // The bitonic sort is shared-memory-bandwidth bound (log^2 passes over the list), so it runs
+  // on the k winners only: the k-th largest packed key (all keys are distinct) is found by
+  // bisection over the list in shared memory, and the entries >= it are compacted in place.
+  if (nc > k) {
+    u64 lo = 0ull, hi = ~0ull;  // invariant: count(cand >= lo) >= k
+    while (lo < hi) {
+      const u64 mid = lo + ((hi - lo) >> 1) + 1ull;
+      int c = 0;
+      for (int i = tid; i < nc; i += kRpnThreads) c += cand[i] >= mid;
+      if (block_sum(c, scratch) >= k) lo = mid;
+      else hi = mid - 1ull;
+    }
+    const u64 kth = lo;
+    int written = 0;  // uniform
+    for (int i0 = 0; i0 < nc; i0 += kRpnThreads) {
+      const int i = i0 + tid;
+      const u64 e = i < nc ? cand[i] : 0ull;
+      const bool t = i < nc && e >= kth;
+      const uint32_t tm = __ballot_sync(0xffffffffu, t);
+      __syncthreads();  // every entry of this chunk is in a register; scratch free
+      if ((tid & 31) == 0) scratch[tid >> 5] = __popc(tm);
+      __syncthreads();
+      int before = 0, chunk = 0;
+      for (int w = 0; w < kRpnThreads / 32; ++w) {
+        const int cw = scratch[w];
+        before += w < (tid >> 5) ? cw : 0;
+        chunk += cw;
+      }
+      if (t) cand[written + before + __popc(tm & ((1u << (tid & 31)) - 1))] = e;  // dst <= src
+      written += chunk;
+    }
+    __syncthreads();
+    nc = k;
+  }
   int npad = 2;
   while (npad < nc) npad <<= 1;
   for (int i = nc + tid; i < npad; i += kRpnThreads) cand[i] = 0ull;  // padding sorts last
