@@ -310,7 +310,7 @@ nms_fused_kernel(const float4* __restrict__ boxes, const float* __restrict__ sco
   u64* keys = reinterpret_cast<u64*>(fused_smem);      // aliases sb during the sort
   __shared__ uint32_t remv[B200_NMS_MAX_SEG / 32];
   __shared__ u64 keepbits[kMaxTiles];
-  __shared__ u64 diag[kTile];
+  __shared__ u64 diag[2][kTile];  // double-buffered: tile i+1's words are computed during tile i's chain
   __shared__ float4 kb[kTile];
   __shared__ float ka[kTile];
   __shared__ float2 kbc[kTile];  // (x centre, x reach) of the tile's kept boxes
@@ -389,6 +389,28 @@ nms_fused_kernel(const float4* __restrict__ boxes, const float* __restrict__ sco
   const int chunk_boxes = can_stop ? kChunkBoxes : nb * kTile;
   int nk = 0;  // boxes in kl (uniform)
   bool done = false;
+  int diag_tile = -1;  // tile whose diagonal words sit in diag[diag_tile & 1] (uniform)
+  // work item (row r, column group cg) of a tile's 64 x 64 diagonal block: CPT columns > r, the G
+  // lanes of a row OR their bits together (they are consecutive lanes of one warp)
+  auto diag_item = [&](int tbase, int trows, u64 tgone, int item, u64* dbuf) {
+    const int r = item / G, cg = item % G;
+    u64 bits = 0;
+    if (r < trows && !((tgone >> r) & 1ull)) {
+      const float4 a = sb[tbase + r];
+      const float area_a = legacy_area(a);
+#pragma unroll 4
+      for (int k = 0; k < CPT; ++k) {
+        const int c = cg * CPT + k;
+        if (c > r && c < trows) {
+          const float4 b = sb[tbase + c];
+          if (suppresses(a, area_a, b, legacy_area(b), thresh)) bits |= 1ull << c;
+        }
+      }
+    }
+#pragma unroll
+    for (int d = G / 2; d > 0; d >>= 1) bits |= __shfl_xor_sync(0xffffffffu, bits, d);
+    if (cg == 0) dbuf[r] = bits;
+  };
   for (int c0 = 0; c0 < n && !done; c0 += chunk_boxes) {
     const int c1 = min(n, c0 + chunk_boxes);
     if (can_stop) {
@@ -457,33 +479,22 @@ nms_fused_kernel(const float4* __restrict__ boxes, const float* __restrict__ sco
       const u64 live_mask = nrows == 64 ? ~0ull : ((1ull << nrows) - 1);
       if ((gone0 & live_mask) == live_mask) continue;  // whole tile already removed (uniform)
 
-      // (a) diagonal words: thread (row r, column group cg) tests CPT columns > r
-      {
-        const int r = tid / G, cg = tid % G;
-        u64 bits = 0;
-        if (r < nrows && !((gone0 >> r) & 1ull)) {
-          const float4 a = sb[base + r];
-          const float area_a = legacy_area(a);
-#pragma unroll 4
-          for (int k = 0; k < CPT; ++k) {
-            const int c = cg * CPT + k;
-            if (c > r && c < nrows) {
-              const float4 b = sb[base + c];
-              if (suppresses(a, area_a, b, legacy_area(b), thresh)) bits |= 1ull << c;
-            }
-          }
-        }
-#pragma unroll
-        for (int d = G / 2; d > 0; d >>= 1) bits |= __shfl_xor_sync(0xffffffffu, bits, d);
-        if (cg == 0) diag[r] = bits;
+      // (a) diagonal words of tile i -- unless they were already produced during the chain of
+      // the previous tile (below)
+      if (diag_tile != i) {
+        diag_item(base, nrows, gone0, tid, diag[i & 1]);
+        __syncthreads();
       }
-      __syncthreads();
-      // (b) in-tile chain
+      // (b) in-tile chain on thread 0; meanwhile warps >= 1 compute the diagonal words of tile
+      // i+1 (pure pairwise facts: rows that turn out to be removed are simply not used)
+      const int nbase = base + kTile;
+      const bool pre = nbase < n;  // uniform
       if (tid == 0) {
+        const u64* dg = diag[i & 1];
         u64 gone = gone0, kept = 0;
 #pragma unroll 8
         for (int r = 0; r < nrows; ++r) {
-          const u64 d = diag[r];
+          const u64 d = dg[r];
           if (!((gone >> r) & 1ull)) {
             kept |= 1ull << r;
             gone |= d;
@@ -491,7 +502,12 @@ nms_fused_kernel(const float4* __restrict__ boxes, const float* __restrict__ sco
         }
         s_kept = kept;
         s_nkept += __popcll(kept);
+      } else if (pre && tid >= 32) {
+        const int nrows2 = min(kTile, n - nbase);
+        for (int item = tid - 32; item < kThreads; item += kThreads - 32)
+          diag_item(nbase, nrows2, 0ull, item, diag[(i + 1) & 1]);
       }
+      if (pre) diag_tile = i + 1;
       __syncthreads();
       const u64 kept = s_kept;
       const int m = __popcll(kept);
