@@ -1,4 +1,4 @@
-// L2 -> SM read bandwidth probe.  Every warp instruction reads 32 x 16 B split into groups of
+// L2 -> SM read bandwidth probe (nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o l2bw l2bw.cu).  Every warp instruction reads 32 x 16 B split into groups of
 // `seg` lanes; each group reads seg*16 contiguous bytes at a pseudo-random, seg*16-aligned place of
 // an L2-resident buffer (seg = 32: one 512 B run; 16: two 256 B runs -- the RoIAlign march
 // pattern; 8: four 128 B runs).  `ilp` independent loads are issued before any is consumed.
