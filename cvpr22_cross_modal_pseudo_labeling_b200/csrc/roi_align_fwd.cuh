@@ -87,4 +87,9 @@ __device__ __forceinline__ void tile_copy_in(float* tile, const float* __restric
 int launch_forward_sep(const LevelTable& lt, int C, const float* rois, int64_t n_rois, int PH, int PW, float* out,
                        float* out_mean, int32_t* out_levels, int variant, cudaStream_t st);
 
+// roi_align_fwd_rows.cu
+bool rows_kernel_applies(const LevelTable& lt, int C, int PH, int PW);
+int launch_forward_rows(const LevelTable& lt, int C, const float* rois, int64_t n_rois, float* out, float* out_mean,
+                        int32_t* out_levels, int variant, cudaStream_t st);
+
 }  // namespace b200

@@ -1,0 +1,189 @@
+"""CPU emulation of the table builder + consumer arithmetic of csrc/roi_align_fwd_rows.cu.
+
+Transcribes build_rows_tab() lane by lane (numpy, fp32) and evaluates the x pass / y pass exactly
+as the consumer threads do, then compares with the C oracle (oracle.pooler_forward).  It checks the
+ALGORITHM (list construction, tap merging, row entries, runs), not the CUDA transcription; the
+GPU parity tests do that.  Test infrastructure only (imports oracle/).
+    python scripts/emulate_rows_tables.py [n_rois]
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import oracle  # noqa: E402
+import synth  # noqa: E402
+
+f32 = np.float32
+P, NS = 7, 14
+
+
+def axis_sample(start, p, binsz, i, grid, extent):
+    pos = f32(start + f32(f32(p) * binsz))
+    pos = f32(pos + f32(f32(f32(f32(i) + f32(0.5)) * binsz) / f32(grid)))
+    ok = not (pos < f32(-1.0) or pos > f32(extent))
+    if pos <= 0:
+        pos = f32(0)
+    lo = int(pos)
+    if lo >= extent - 1:
+        hi = lo = extent - 1
+        pos = f32(lo)
+    else:
+        hi = lo + 1
+    l = f32(pos - f32(lo))
+    h = f32(f32(1.0) - l)
+    return lo, hi, l, h, ok
+
+
+def build_axis(start, binsz, extent):
+    """one half-warp of build_rows_tab: returns (list coords, per-bin merged taps [(idx, w)])"""
+    lo = [0] * 16; hi = [0] * 16; wl = [f32(0)] * 16; wh = [f32(0)] * 16
+    for hl in range(NS):
+        a, b, l, h, ok = axis_sample(start, hl >> 1, binsz, hl & 1, 2, extent)
+        if ok:
+            lo[hl], hi[hl], wl[hl], wh[hl] = a, b, l, h
+    nnew = [0] * 16
+    for hl in range(16):
+        n = 1 if lo[hl] == hi[hl] else 2
+        if hl > 0:
+            if lo[hl] == lo[hl - 1] and hi[hl] == hi[hl - 1]:
+                n = 0
+            elif lo[hl] == hi[hl - 1]:
+                n = 1
+        if hl >= NS:
+            n = 0
+        nnew[hl] = n
+    scan = list(np.cumsum(nnew))
+    nlist = scan[15]
+    coords = [None] * nlist
+    for hl in range(NS):
+        if nnew[hl] >= 1:
+            coords[scan[hl] - 1] = hi[hl]
+        if nnew[hl] == 2:
+            coords[scan[hl] - 2] = lo[hl]
+    jhi = [scan[hl] - 1 for hl in range(16)]
+    jlo = [jhi[hl] if lo[hl] == hi[hl] else jhi[hl] - 1 for hl in range(16)]
+    w_lo = [f32(0) if lo[hl] == hi[hl] else wh[hl] for hl in range(16)]
+    w_hi = [f32(wl[hl] + wh[hl]) if lo[hl] == hi[hl] else wl[hl] for hl in range(16)]
+    bins = []
+    for b in range(P):
+        sa, sb = 2 * b, 2 * b + 1
+        idx = [jlo[sa], jhi[sa], jlo[sb], jhi[sb]]
+        w = [w_lo[sa], w_hi[sa], w_lo[sb], w_hi[sb]]
+        for k in range(1, 4):
+            for j in range(k):
+                if idx[k] == idx[j]:
+                    w[j] = f32(w[j] + w[k])
+                    w[k] = f32(0)
+        bins.append([(idx[k], w[k]) for k in range(4) if w[k] != 0])
+    assert all(c is not None for c in coords)
+    return coords, bins
+
+
+def runs_of(cols):
+    runs = []
+    for j, x in enumerate(cols):
+        if j == 0 or x != cols[j - 1] + 1:
+            runs.append([j, x, 1])
+        else:
+            runs[-1][2] += 1
+    return runs
+
+
+def emulate_roi(feats, roi, scales, k_min, k_max, stats):
+    """feats: list of [B, H, W, C] fp32 arrays (NHWC)"""
+    b = int(roi[0])
+    x1, y1, x2, y2 = [f32(v) for v in roi[1:]]
+    lvl = int(oracle.level_map(np.asarray([roi], dtype=np.float32), k_min, k_max)[0]) if len(feats) > 1 else 0
+    C = feats[0].shape[-1]
+    if lvl < 0:
+        return np.zeros((C, P, P), np.float32), lvl
+    f = feats[lvl]
+    H, W = f.shape[1], f.shape[2]
+    sc = f32(scales[lvl])
+    sw, sh = f32(x1 * sc), f32(y1 * sc)
+    rw = max(f32(f32(x2 * sc) - sw), f32(1.0))
+    rh = max(f32(f32(y2 * sc) - sh), f32(1.0))
+    bh, bw = f32(rh / f32(P)), f32(rw / f32(P))
+    rows, ybins = build_axis(sh, bh, H)
+    cols, xbins = build_axis(sw, bw, W)
+    # slot image of every list row: the runs copied to compact positions
+    runs = runs_of(cols)
+    assert sum(r[2] for r in runs) == len(cols) and len(runs) <= 28
+    stats["runs"] += len(runs); stats["rows"] += len(rows); stats["cols"] += len(cols)
+    wy = np.zeros((len(rows), 8), np.float32)
+    for ph, taps in enumerate(ybins):
+        for idx, w in taps:
+            assert wy[idx, ph] == 0
+            wy[idx, ph] = f32(f32(0.25) * w)
+    acc = np.zeros((P, P, C), np.float32)
+    for i, y in enumerate(rows):
+        slot = np.zeros((28, C), np.float32)
+        for pos, col, ln in runs:
+            slot[pos:pos + ln] = f[b, y, col:col + ln]
+        mask = [ph for ph in range(P) if wy[i, ph] != 0]
+        if mask and (mask[-1] - mask[0] + 1) > 2:
+            stats["generic"] += 1
+        for pw, taps in enumerate(xbins):
+            u = np.zeros(C, np.float32)
+            for idx, w in taps:
+                u = (u + w * slot[idx]).astype(np.float32)
+            if not mask:
+                continue
+            blo = mask[0]
+            if mask[-1] - blo + 1 <= 2:
+                acc[blo, pw] += wy[i, blo] * u
+                if blo + 1 < P:
+                    acc[blo + 1, pw] += wy[i, blo + 1] * u
+            else:
+                for ph in range(P):
+                    if wy[i, ph] != 0:
+                        acc[ph, pw] += wy[i, ph] * u
+    return acc.transpose(2, 0, 1), lvl
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 300
+    rng = np.random.default_rng(7)
+    B, C = 2, 8
+    shapes = synth.fpn_shapes(400, 672)
+    feats_nchw = [rng.standard_normal((B, C, h, w)).astype(np.float32) for (h, w) in shapes]
+    feats_nhwc = [np.ascontiguousarray(f.transpose(0, 2, 3, 1)) for f in feats_nchw]
+    rois = synth.make_rois(rng, n, B, 672, 400, smin=2, smax=700, degenerate=0.05)
+    # extra edge cases: outside the image, tiny, huge, touching borders, malformed
+    extra = np.array([
+        [0, -50, -50, -20, -20], [0, 700, 450, 800, 500], [1, 660, 390, 690, 420], [0, -30, 100, 40, 180],
+        [1, 100, 100, 100.5, 100.5], [0, 0, 0, 671, 399], [1, 300, 200, 290, 190], [0, 10.3, 20.7, 12.1, 22.2],
+        [0, -200, -200, 900, 700], [1, 640, 0, 900, 30], [0, 0, 380, 30, 600], [1, 5, 5, 9, 300],
+    ], dtype=np.float32)
+    rois = np.concatenate([rois, extra]).astype(np.float32)
+    scales = synth.FPN_SCALES
+    k_min, k_max = -np.log2(scales[0]), -np.log2(scales[-1])
+    want, wl = oracle.pooler_forward(feats_nchw, rois, scales, P, P, 2)
+    stats = dict(runs=0, rows=0, cols=0, generic=0)
+    worst = 0.0
+    for i, roi in enumerate(rois):
+        got, lvl = emulate_roi(feats_nhwc, roi, scales, k_min, k_max, stats)
+        assert lvl == wl[i], (i, lvl, wl[i])
+        err = np.abs(got - want[i]).max() / max(1e-6, np.abs(want[i]).max())
+        assert np.allclose(got, want[i], rtol=1e-5, atol=2e-6), (i, roi, err)
+        worst = max(worst, err)
+    m = len(rois)
+    print("ok: %d RoIs, worst rel err %.2e; per RoI: rows %.1f cols %.1f runs %.2f; generic rows %d" %
+          (m, worst, stats["rows"] / m, stats["cols"] / m, stats["runs"] / m, stats["generic"]))
+    # single-level pooler with wide RoIs (sparse taps -> many runs)
+    f1 = [feats_nchw[1]]
+    big = synth.make_rois(rng, 60, B, 672, 400, smin=100, smax=700, degenerate=0.0)
+    want1, _ = oracle.pooler_forward(f1, big, (scales[1],), P, P, 2)
+    stats = dict(runs=0, rows=0, cols=0, generic=0)
+    for i, roi in enumerate(big):
+        got, _ = emulate_roi([feats_nhwc[1]], roi, (scales[1],), 0, 0, stats)
+        assert np.allclose(got, want1[i], rtol=1e-5, atol=2e-6), (i, roi)
+    print("ok: single level, %d wide RoIs; runs per RoI %.1f" % (len(big), stats["runs"] / len(big)))
+
+
+if __name__ == "__main__":
+    main()
