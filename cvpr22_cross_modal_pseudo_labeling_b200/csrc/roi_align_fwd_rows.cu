@@ -37,11 +37,11 @@ constexpr int kBins = kP * kP;                   // 49
 constexpr int kMaxList = 2 * kNS;                // distinct tap rows / columns of a RoI, at most
 constexpr int kRC = 256;                         // channels
 constexpr int kPxBytes = kRC * 4;                // one pixel, all channels
-constexpr int kSlotBytes = kMaxList * kPxBytes;  // one tap row: the tapped columns, compacted
-constexpr int kSlots = 6;                        // ring of tap rows
-constexpr int kRingBytes = kSlots * kSlotBytes;
+constexpr int kRingPx = 168;                     // byte ring of tap rows, in pixels (1 KB units)
+constexpr int kRingBytes = kRingPx * kPxBytes;
+constexpr int kNBar = 16;                        // ring entries in flight, at most (barrier pairs)
+constexpr int kHist = 64;                        // placement history the planner keeps (> kNBar + kMaxList)
 constexpr int kTabs = 4;                         // RoI tables in flight
-constexpr int kMaxCopyWarps = 4;
 constexpr int kWarpsPerBin = kRC / 4 / 32;       // 2
 constexpr int kConsWarps = kP * kWarpsPerBin;    // 14
 constexpr int kConsThreads = kConsWarps * 32;    // 448
@@ -53,6 +53,12 @@ constexpr int kTileFloats = kRC * kBins;
 // Entries are grouped by b (ascending), so the consumers' accumulator indices are compile-time
 // constants; a tap row feeding more than two output rows (bins narrower than ~1.3 pixels) is simply
 // listed -- and copied -- once per pair.
+// `place`: where the planner put the entry in the byte ring; `dep`: the copy may be issued once every
+// ring entry with a sequence number < dep has been given back (entries are given back in order)
+struct __align__(16) RingEntry {
+  float w0, w1;
+  uint32_t place, dep;
+};
 struct __align__(16) RoiTab {
   int nent, ncols, nruns, level;
   int batch, width, pad0, pad1;
@@ -60,11 +66,8 @@ struct __align__(16) RoiTab {
   float wx[kP][4];  // its weight (0 for unused entries)
   int nk[8];        // merged tap columns per bin
   int gend[8];      // entries [gend[b-1], gend[b]) feed output rows b, b + 1
-  float2 ent_w[kMaxList];
+  RingEntry ent[kMaxList];
   int ent_y[kMaxList];    // feature row of entry e
-  float wy[kMaxList][8];  // weight (x 1/4) of list row i for output row ph
-  int rowy[kMaxList];     // feature row of list entry i
-  int colx[kMaxList];     // feature column of list entry j
   int run_pos[kMaxList], run_col[kMaxList], run_len[kMaxList];  // runs of consecutive tapped columns
 };
 
@@ -107,6 +110,20 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t phase) {
 __device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// shared -> global bulk store (TMA, one thread), tracked by the thread's bulk async-group
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, uint32_t src_smem, uint32_t bytes, uint64_t policy) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst_gmem),
+               "r"(src_smem), "r"(bytes), "l"(policy)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
 __device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 1, %0;" ::"n"(kConsThreads) : "memory"); }
 
 struct RoiPlace {
@@ -114,8 +131,21 @@ struct RoiPlace {
 };
 
 // Producer warp: axis tables of RoI r.  Lanes 0-13 own the y samples, lanes 16-29 the x samples.
+// planner-private scratch (one copy; the tables above are what the other warps read)
+struct __align__(16) PlanScratch {
+  float wy[kMaxList][8];  // weight (x 1/4) of list row i for output row ph
+  int rowy[kMaxList];     // feature row of list entry i
+  int colx[kMaxList];     // feature column of list entry j
+  uint32_t hist_place[kHist], hist_size[kHist];  // ring placement of the last kHist entries (pixels)
+};
+
+struct RingPlanner {
+  uint32_t g0;    // ring entries of the RoIs planned so far
+  uint32_t head;  // next free pixel of the ring
+};
+
 __device__ __forceinline__ RoiPlace build_rows_tab(const LevelTable& lt, const float* __restrict__ rois, long long r,
-                                                   RoiTab* tb, int lane) {
+                                                   RoiTab* tb, int lane, RingPlanner& rp, PlanScratch* sc) {
   const RoiHeader h = load_roi(rois, r, lt);
   RoiPlace pl;
   pl.level = h.level;
@@ -165,13 +195,13 @@ __device__ __forceinline__ RoiPlace build_rows_tab(const LevelTable& lt, const f
     if (hl >= d) scan += v;
   }
   const int nrows = __shfl_sync(0xffffffffu, scan, 15), ncols = __shfl_sync(0xffffffffu, scan, 31);
-  int* list = isx ? tb->colx : tb->rowy;
+  int* list = isx ? sc->colx : sc->rowy;
   if (hl < kNS) {
     if (nnew >= 1) list[scan - 1] = hi;
     if (nnew == 2) list[scan - 2] = lo;
   }
   // zero the row-weight table
-  float* wyf = &tb->wy[0][0];
+  float* wyf = &sc->wy[0][0];
   for (int i = lane; i < kMaxList * 8; i += 32) wyf[i] = 0.f;
   // the two taps of this sample as (list index, weight)
   const int jhi = scan - 1, jlo = lo == hi ? jhi : jhi - 1;
@@ -228,7 +258,7 @@ __device__ __forceinline__ RoiPlace build_rows_tab(const LevelTable& lt, const f
     } else {
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        if (w[k] != 0.f) tb->wy[idx[k]][hl] = 0.25f * w[k];
+        if (w[k] != 0.f) sc->wy[idx[k]][hl] = 0.25f * w[k];
     }
   }
   __syncwarp();
@@ -240,7 +270,7 @@ __device__ __forceinline__ RoiPlace build_rows_tab(const LevelTable& lt, const f
     if (lane < nrows) {
 #pragma unroll
       for (int ph = 0; ph < kP; ++ph)
-        if (tb->wy[lane][ph] != 0.f) mask |= 1u << ph;
+        if (sc->wy[lane][ph] != 0.f) mask |= 1u << ph;
     }
     unsigned pk = 0;
 #pragma unroll
@@ -249,7 +279,7 @@ __device__ __forceinline__ RoiPlace build_rows_tab(const LevelTable& lt, const f
         pk |= 1u << b;
         mask &= ~(3u << b);
       }
-    const int y = lane < nrows ? tb->rowy[lane] : 0;
+    const int y = lane < nrows ? sc->rowy[lane] : 0;
 #pragma unroll
     for (int b = 0; b < kP; ++b) {
       const bool f = (pk >> b) & 1u;
@@ -257,16 +287,50 @@ __device__ __forceinline__ RoiPlace build_rows_tab(const LevelTable& lt, const f
       if (f) {
         const int dst = nent + __popc(bal & ((1u << lane) - 1u));
         tb->ent_y[dst] = y;
-        tb->ent_w[dst] = make_float2(tb->wy[lane][b], b + 1 < kP ? tb->wy[lane][b + 1] : 0.f);
+        tb->ent[dst].w0 = sc->wy[lane][b];
+        tb->ent[dst].w1 = b + 1 < kP ? sc->wy[lane][b + 1] : 0.f;
       }
       nent += __popc(bal);
       if (lane == 0) tb->gend[b] = nent;
     }
   }
+  // ring placement: the entries of a RoI all span ncols pixels and are laid one after the other,
+  // wrapping to the start of the ring when the next one would not fit; an entry's copy depends on the
+  // newest earlier entry whose bytes it overwrites (found in the placement history) and on the
+  // entry that last used its barrier pair
+  {
+    const uint32_t s = (uint32_t)ncols;  // >= 1
+    const uint32_t k0 = ((uint32_t)kRingPx - rp.head) / s, kfit = (uint32_t)kRingPx / s;
+    const uint32_t i = (uint32_t)lane;
+    const uint32_t place = i < k0 ? rp.head + i * s : ((i - k0) % kfit) * s;
+    const uint32_t g = rp.g0 + i;
+    if (lane < nent) {
+      sc->hist_place[g % kHist] = place;
+      sc->hist_size[g % kHist] = s;
+    }
+    __syncwarp();
+    if (lane < nent) {
+      uint32_t dep = g >= (uint32_t)kNBar ? g - (uint32_t)kNBar + 1u : 0u;
+#pragma unroll 5
+      for (uint32_t d = 1; d < (uint32_t)kNBar; ++d) {
+        if (d > g) break;
+        const uint32_t e = g - d;
+        const uint32_t pe = sc->hist_place[e % kHist], se = sc->hist_size[e % kHist];
+        if (pe < place + s && place < pe + se) {
+          dep = dep > e + 1u ? dep : e + 1u;
+          break;  // older overlapping entries only give smaller values
+        }
+      }
+      tb->ent[lane].place = place * (uint32_t)kPxBytes;
+      tb->ent[lane].dep = dep;
+    }
+    if (nent > 0) rp.head = __shfl_sync(0xffffffffu, place, nent - 1) + s;
+    rp.g0 += (uint32_t)nent;
+  }
   // runs of consecutive tapped columns: one bulk copy each
   {
-    const int x = lane < ncols ? tb->colx[lane] : 0;
-    const int xp = (lane > 0 && lane < ncols) ? tb->colx[lane - 1] : 0;
+    const int x = lane < ncols ? sc->colx[lane] : 0;
+    const int xp = (lane > 0 && lane < ncols) ? sc->colx[lane - 1] : 0;
     const bool start = lane < ncols && (lane == 0 || x != xp + 1);
     const unsigned smask = __ballot_sync(0xffffffffu, start);
     if (start) {
@@ -299,14 +363,15 @@ roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, long lon
   // (no integer round trip on this pointer: the compiler must keep seeing shared-space addresses,
   // or every access below turns into a generic LD.E / ST.E)
   extern __shared__ __align__(128) unsigned char smem_dyn[];
-  __shared__ __align__(128) uint64_t full_bar[kSlots], empty_bar[kSlots], tab_full[kTabs], tab_empty[kTabs];
+  __shared__ __align__(128) uint64_t full_bar[kNBar], empty_bar[kNBar], tab_full[kTabs], tab_empty[kTabs];
+  __shared__ PlanScratch plan_scratch;
   unsigned char* ring = smem_dyn;
   float* tile = reinterpret_cast<float*>(smem_dyn + (size_t)kRingBytes);
   RoiTab* tabs = reinterpret_cast<RoiTab*>(tile + kTileFloats);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int s = 0; s < kSlots; ++s) {
+    for (int s = 0; s < kNBar; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], kConsWarps);
     }
@@ -320,11 +385,14 @@ roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, long lon
 
   if (warp == kPlanWarp) {
     // ------------------------------- planner: RoI tables ---------------------------------
+    RingPlanner rp;
+    rp.g0 = 0;
+    rp.head = 0;
     int n = 0;
     for (long long r = blockIdx.x; r < n_rois; r += gridDim.x, ++n) {
       const int ti = n % kTabs;
       mbar_wait(&tab_empty[ti], (uint32_t)(((n / kTabs) & 1) ^ 1));  // (a fresh barrier passes)
-      const RoiPlace pl = build_rows_tab(lt, rois, r, tabs + ti, lane);
+      const RoiPlace pl = build_rows_tab(lt, rois, r, tabs + ti, lane, rp, &plan_scratch);
       if (lane == 0 && out_levels) out_levels[r] = pl.level;
       __syncwarp();
       if (lane == 0) mbar_arrive(&tab_full[ti]);
@@ -356,12 +424,13 @@ roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, long lon
         // first entry of this RoI that belongs to this warp
         int i = (int)((cw + kCopyWarps - g0 % kCopyWarps) % kCopyWarps);
         for (; i < nent; i += kCopyWarps) {
-          const uint32_t g = g0 + (uint32_t)i, slot = g % kSlots;
-          mbar_wait(&empty_bar[slot], ((g / kSlots) & 1u) ^ 1u);
-          if (lane == 0) mbar_arrive_expect_tx(&full_bar[slot], size);
+          const uint32_t g = g0 + (uint32_t)i, bi = g % kNBar;
+          const uint32_t place = tb->ent[i].place, dep = tb->ent[i].dep;
+          // (dep - 1 >= g - kNBar, so the parity below names one phase unambiguously)
+          if (dep > 0) mbar_wait(&empty_bar[(dep - 1u) % kNBar], ((dep - 1u) / kNBar) & 1u);
+          if (lane == 0) mbar_arrive_expect_tx(&full_bar[bi], size);
           if (lane < nruns)
-            bulk_g2s(ring + slot * kSlotBytes + my_pos, gbase + (size_t)tb->ent_y[i] * width * kPxBytes, my_len,
-                     &full_bar[slot]);
+            bulk_g2s(ring + place + my_pos, gbase + (size_t)tb->ent_y[i] * width * kPxBytes, my_len, &full_bar[bi]);
         }
         g0 += (uint32_t)nent;
       }
@@ -380,6 +449,7 @@ roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, long lon
   uint32_t ring_a = smem_u32(ring) + q * 16, full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
   uint32_t tabs_a = smem_u32(tabs);
   asm volatile("" : "+r"(ring_a), "+r"(full_a), "+r"(empty_a), "+r"(tabs_a));
+  const uint64_t store_policy = policy_evict_first();
   uint32_t g = 0;   // ring entry to load into registers next
   uint32_t rg = 0;  // ring entry to give back next
   int n = 0;
@@ -402,10 +472,9 @@ roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, long lon
     v0.lo = v0.hi = make_float2(0.f, 0.f);
     v1 = v2 = v3 = v0;
     // the tap columns of bin pw of the next ring entry -> registers
-    auto load_row = [&]() {
-      const uint32_t bi = g % kSlots;
-      mbar_wait_a(full_a + 8u * bi, (g / kSlots) & 1u);
-      const uint32_t off = bi * kSlotBytes;
+    auto load_row = [&](uint32_t off) {
+      const uint32_t bi = g % kNBar;
+      mbar_wait_a(full_a + 8u * bi, (g / kNBar) & 1u);
       if (kProbe == 0) {
         v0 = lds_v4(c0 + off);
         v1 = lds_v4(c1 + off);
@@ -414,13 +483,13 @@ roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, long lon
       }
       ++g;
     };
-    if (nent > 0) load_row();
-    uint32_t ent_a = tb_a + (uint32_t)offsetof(RoiTab, ent_w);
-    const uint32_t ent_last = ent_a + 8u * (uint32_t)(nent - 1);
+    uint32_t ent_a = tb_a + (uint32_t)offsetof(RoiTab, ent);
+    const uint32_t ent_last = ent_a + 16u * (uint32_t)(nent - 1);
+    if (nent > 0) load_row((uint32_t)lds_i32(ent_a + 8u));
 #pragma unroll
     for (int b = 0; b < kP; ++b) {
-      const uint32_t end_a = tb_a + (uint32_t)offsetof(RoiTab, ent_w) + 8u * (uint32_t)lds_i32(tb_a + (uint32_t)offsetof(RoiTab, gend) + 4u * b);
-      for (; ent_a < end_a; ent_a += 8) {
+      const uint32_t end_a = tb_a + (uint32_t)offsetof(RoiTab, ent) + 16u * (uint32_t)lds_i32(tb_a + (uint32_t)offsetof(RoiTab, gend) + 4u * b);
+      for (; ent_a < end_a; ent_a += 16) {
         // x pass: the tap columns reduced to one value per channel
         float2 ulo = make_float2(0.f, 0.f), uhi = ulo;
         if (kProbe == 0) {
@@ -437,11 +506,11 @@ roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, long lon
           }
         }
         const float2 w = lds_f2(ent_a);
-        // the registers are free again: fetch the next row while this one is accumulated
-        if (ent_a < ent_last) load_row();
+        // this entry has been read: give it back, then fetch the next row while this one is accumulated
         __syncwarp();
-        if (lane == 0) mbar_arrive_a(empty_a + 8u * (rg % kSlots));  // this entry has been read: give it back
+        if (lane == 0) mbar_arrive_a(empty_a + 8u * (rg % kNBar));
         ++rg;
+        if (ent_a < ent_last) load_row((uint32_t)lds_i32(ent_a + 16u + 8u));
         // y pass
         const float2 w0 = make_float2(w.x, w.x);
         alo[b] = __ffma2_rn(w0, ulo, alo[b]);
@@ -461,7 +530,8 @@ roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, long lon
     if (lane == 0) mbar_arrive(&tab_empty[ti]);
 
     // ---- epilogue: registers -> [256 x 49] tile -> one contiguous block of the output -------
-    bar_consumers();  // the copy-out of the previous RoI has left the tile
+    if (tid == 0) bulk_wait_read();  // the bulk store of the previous RoI has read the tile
+    bar_consumers();
     {
       // lane groups of 8 write different channels of their quad in one instruction (rotation by
       // lane / 8): 32 lanes then hit 32 different banks (quad stride 196 = 4 mod 32, channel 49 = 17)
@@ -493,12 +563,12 @@ roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, long lon
         tc[3][ph * kP] = d;
       }
     }
+    // one contiguous 50 KB block of the NCHW output: a single bulk store (TMA) drains the tile while
+    // the consumers are already in the next RoI's rows
+    fence_proxy_async();  // this thread's tile writes -> visible to the async proxy
     bar_consumers();
     {
-      const float4* src = reinterpret_cast<const float4*>(tile);
-      float4* dst = reinterpret_cast<float4*>(out + (size_t)r * kTileFloats);
-#pragma unroll
-      for (int i = 0; i < kTileFloats / 4 / kConsThreads; ++i) __stcs(dst + tid + i * kConsThreads, src[tid + i * kConsThreads]);
+      if (tid == 0) bulk_s2g(out + (size_t)r * kTileFloats, smem_u32(tile), kTileFloats * 4, store_policy);
       if (out_mean && tid < kRC) {
         const float* row = tile + tid * kBins;
         float s = 0.f;
@@ -508,6 +578,7 @@ roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, long lon
       }
     }
   }
+  if (tid == 0) bulk_wait_all();  // the last store must have left shared memory before the CTA exits
 }
 
 }  // namespace
@@ -526,15 +597,15 @@ int launch_forward_rows(const LevelTable& lt, int C, const float* rois, int64_t 
 #define B200_ROWS(CW, PROBE)                                                                                      \
   do {                                                                                                            \
     static SmemHighWater hw;                                                                                      \
-    int rc = ensure_dynamic_smem(roi_align_fwd_rows<CW, PROBE>, kRowsSmem, &hw, "roi_align rows: smem attribute"); \
+    int rc = ensure_dynamic_smem(roi_align_fwd_rows<CW, PROBE>, kRowsSmem, &hw, "roi_align rows: smem");          \
     if (rc != B200_OK) return rc;                                                                                 \
     roi_align_fwd_rows<CW, PROBE><<<(unsigned)grid, kConsThreads + 32 + 32 * CW, kRowsSmem, st>>>(                \
         lt, rois, (long long)n_rois, out, out_mean, out_levels);                                                  \
   } while (0)
-  // variant (tuning hook of b200_debug_set): bit 5 = two copy warps instead of four, bit 6 = copy-engine probe
-  if (variant & 64) B200_ROWS(4, 1);
-  else if (variant & 32) B200_ROWS(2, 0);
-  else B200_ROWS(4, 0);
+  // variant (tuning hook of b200_debug_set): bit 5 = four copy warps instead of two, bit 6 = copy-engine probe
+  if (variant & 64) B200_ROWS(2, 1);
+  else if (variant & 32) B200_ROWS(4, 0);
+  else B200_ROWS(2, 0);
 #undef B200_ROWS
   B200_CHECK_LAUNCH("roi_align_fwd_rows");
   return B200_OK;

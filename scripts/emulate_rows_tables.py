@@ -185,5 +185,52 @@ def main():
     print("ok: single level, %d wide RoIs; runs per RoI %.1f" % (len(big), stats["runs"] / len(big)))
 
 
+
+
+def check_ring_planner(n_rois=3000, seed=3):
+    """The planner's byte-ring placement (build_rows_tab, 'ring placement'): no entry may overwrite an
+    earlier entry that is not guaranteed to have been given back (sequence number >= dep), entries stay
+    inside the ring, and dep - 1 >= g - kNBar (the parity of the empty barrier is then unambiguous)."""
+    RING, NBAR, HIST = 168, 16, 64
+    rng = np.random.default_rng(seed)
+    g0, head = 0, 0
+    hist_place = [0] * HIST
+    hist_size = [0] * HIST
+    placed = []  # (place, size) by sequence number
+    for _ in range(n_rois):
+        s = int(rng.integers(1, 29))
+        nent = int(rng.integers(0, 29))
+        k0, kfit = (RING - head) // s, RING // s
+        places = []
+        for i in range(nent):
+            place = head + i * s if i < k0 else ((i - k0) % kfit) * s
+            places.append(place)
+            hist_place[(g0 + i) % HIST] = place
+            hist_size[(g0 + i) % HIST] = s
+        for i in range(nent):
+            g = g0 + i
+            place = places[i]
+            dep = g - NBAR + 1 if g >= NBAR else 0
+            for d in range(1, NBAR):
+                if d > g:
+                    break
+                e = g - d
+                pe, se = hist_place[e % HIST], hist_size[e % HIST]
+                if pe < place + s and place < pe + se:
+                    dep = max(dep, e + 1)
+                    break
+            assert 0 <= place and place + s <= RING
+            assert dep <= g and (dep == 0 or dep - 1 >= g - NBAR)
+            for e in range(dep, g):
+                pe, se = placed[e]
+                assert not (pe < place + s and place < pe + se), (g, e)
+            placed.append((place, s))
+        if nent:
+            head = places[-1] + s
+        g0 += nent
+    print("ok: ring planner, %d entries" % len(placed))
+
+
 if __name__ == "__main__":
     main()
+    check_ring_planner()
