@@ -548,7 +548,7 @@ def run_gpu(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "images_per_gpu": B_IMG, "rois_per_image": R_IMG,
                        "feature_layout": "channels_last (NHWC memory, logical [B,C,H,W])",
-                       "roi_align_math": ("fast: separable FMA evaluation, <= 1e-5 rel of ROIAlign_cpu (b200_roi_align_forward_fast)"
+                       "roi_align_math": ("fast: separable FMA evaluation (row-streaming kernel), <= 1e-5 rel of ROIAlign_cpu (b200_roi_align_forward_fast)"
                                           if args.math == "fast" else "exact: bit-identical to ROIAlign_cpu (b200_roi_align_forward)"),
                        "l2": "inputs (1.46 GB features/GPU) exceed the 126 MB L2; no flush needed",
                        "images_per_sec": world * B_IMG / (ms_step * 1e-3),
@@ -560,7 +560,7 @@ def run_gpu(args):
                     "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(rec_h.numel() * 4 + cnt_h.numel() * 4) // world},
             "gpu_launches": args.steps * 7,  # nms, select, pool7, softmax match, colmax match, decode, pool14
             "kernel_ms": kms,
-            "roofline": {"kernel": "%s (box pooler 7x7)" % ("roi_align_fwd_sep" if args.math == "fast" else "roi_align_fwd_march"), "bound": "hbm", "achieved": achieved,
+            "roofline": {"kernel": "%s (box pooler 7x7)" % ("roi_align_fwd_rows" if args.math == "fast" else "roi_align_fwd_march"), "bound": "hbm", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                          "algorithmic_bytes": int(algo), "f_touched_bytes": int(ft), "traffic": traffic},

@@ -323,9 +323,10 @@ int launch_forward(const LevelTable& lt, int layout, int C, const float* rois, i
   B200_REQUIRE(n_rois * ((C + 15) / 16) < (int64_t)1 << 31, "roi_align: too many RoIs for one launch");
   if (march_ok) {
     if constexpr (!kExact) {
-      // fast math: the row-streaming kernel for the FPN box pooler shape (roi_align_fwd_rows.cu;
-      // g_variant & 16, tuning hook), else the separable marching kernel (roi_align_fwd_sep.cu)
-      if ((g_variant & 16) && rows_kernel_applies(lt, C, PH, PW))
+      // fast math: the row-streaming kernel for the FPN box pooler shape (roi_align_fwd_rows.cu), else
+      // -- or when the tuning hook sets g_variant & 16 -- the separable marching kernel
+      // (roi_align_fwd_sep.cu)
+      if (!(g_variant & 16) && rows_kernel_applies(lt, C, PH, PW))
         return launch_forward_rows(lt, C, rois, n_rois, out, out_mean, out_levels, g_variant, st);
       return launch_forward_sep(lt, C, rois, n_rois, PH, PW, out, out_mean, out_levels, g_variant & 15, st);
     } else {

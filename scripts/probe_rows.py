@@ -1,5 +1,5 @@
-"""Probe: row-streaming RoIAlign forward (variant 16) against the separable marching kernel
-(variant 0) on the box-pooler microbench (16 images x 1000 RoIs, 256 channels, 7x7)."""
+"""Probe: row-streaming RoIAlign forward (variant 0, the default) against the separable marching kernel
+(variant 16) on the box-pooler microbench (16 images x 1000 RoIs, 256 channels, 7x7)."""
 import os
 import sys
 
@@ -31,7 +31,7 @@ feats = [torch.randn((B, C, h, w), device="cuda", generator=g).contiguous(memory
 rois = torch.from_numpy(synth.make_rois(rng, 1000, B)).cuda()
 r1 = rois.clone(); r1[:, 0] = 0; r1[:, 1] = 200; r1[:, 2] = 200; r1[:, 3] = 264; r1[:, 4] = 264
 r0 = rois.clone(); r0[:, 0] = 0
-variants = [int(v) for v in sys.argv[1].split(",")] if len(sys.argv) > 1 else [0, 16]
+variants = [int(v) for v in sys.argv[1].split(",")] if len(sys.argv) > 1 else [16, 0]
 for v in variants:
     _ext.debug_set(False, False, v)
     t, tmin = timeit(lambda: _forward(feats, synth.FPN_SCALES, rois, (7, 7), 2))

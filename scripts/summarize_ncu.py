@@ -70,7 +70,7 @@ def main():
                         if k in rec and rec[k] != "":
                             f.write("  %-90s %s %s\n" % (k, rec[k], units.get(k, "")))
                     f.write("\n")
-            if "roi_align_fwd_sep" in name and recs:
+            if "roi_align_fwd_rows" in name and recs:
                 rec = recs[0]
                 conv = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}
                 rd = float(rec["dram__bytes_read.sum"]) * conv[units["dram__bytes_read.sum"]]

@@ -12,7 +12,8 @@ from tests import synth
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-5
-ROWS = 16  # b200_debug_set variant bit that selects the kernel
+ROWS = 0   # the default fast path for this shape
+SEP = 16   # b200_debug_set variant bit that forces the separable marching kernel instead
 
 
 def _ext():
@@ -58,7 +59,9 @@ def test_rows_kernel_matches_oracle_multilevel():
     np.testing.assert_allclose(got, want, rtol=RTOL, atol=1e-6)
     assert np.all(got[-1] == 0) and np.all(got[len(rois) - len(EDGE)] == 0)      # fully outside
     # and really a different kernel from the marching one: bitwise differences are expected somewhere
-    ref, _ = _fwd(feats, synth.FPN_SCALES, torch.from_numpy(rois).cuda(), 0)
+    ref, _ = _fwd(feats, synth.FPN_SCALES, torch.from_numpy(rois).cuda(), SEP)
+    assert not np.array_equal(got, ref.cpu().numpy())
+    np.testing.assert_allclose(ref.cpu().numpy(), want, rtol=RTOL, atol=1e-6)      # the fallback stays covered at 256 channels
     np.testing.assert_allclose(got, ref.cpu().numpy(), rtol=2 * RTOL, atol=2e-6)
 
 
