@@ -9,21 +9,31 @@
 // instead of by registers:
 //   * persistent CTAs, one per SM; CTA b walks RoIs b, b + gridDim, ... (image-major order is kept,
 //     so an image's pyramid is still pulled from HBM about once);
-//   * a producer warp builds the RoI's axis tables and streams every DISTINCT tap row of the RoI
-//     -- the run(s) of tapped columns x all 256 channels, contiguous in NHWC -- into a ring of
-//     shared-memory slots with cp.async.bulk (1-D TMA, up to 28 KB per request, mbarrier
-//     complete_tx); it runs ahead across RoI boundaries, so ~100 KB per SM are in flight;
-//   * 14 consumer warps: thread = (channel quad, output column pw).  Per arriving row a thread
-//     reduces the (<= 4, duplicates merged) tap columns of its bin to one float4 (the x pass),
-//     then adds it into the accumulators of the (<= 2, else generic path) output rows that tap
-//     this row (the y pass).  All 49 bins x 4 channels of a thread stay in registers; nothing
-//     waits on global memory.
+//   * two planner warps (alternating RoIs, four RoIs ahead) build a RoI's tables: the distinct tap
+//     rows / columns, the merged x weights of every bin, the ring entries -- one per (tap row, pair
+//     of output rows it feeds), grouped by output row -- and, holding a placement turn, where each
+//     entry goes in a 168 KB byte ring and which earlier entry's release its copy must wait for;
+//   * two copy warps (entry g belongs to warp g % 2) stream every entry -- the run(s) of tapped
+//     columns x all 256 channels, contiguous in NHWC -- into the ring with cp.async.bulk (1-D TMA,
+//     up to 28 KB per request, mbarrier complete_tx); up to 16 entries (~9 at the mean patch size,
+//     ~160 KB per SM) are in flight, across RoI boundaries;
+//   * 14 consumer warps: thread = (channel quad, output column pw).  Per arriving entry a thread
+//     reduces the (<= 4, duplicates merged) tap columns of its bin to one value per channel (the x
+//     pass, FMUL2 / FFMA2: two fp32 lanes per issue slot), gives the entry back, prefetches the next
+//     entry's columns into the same registers, then adds into the accumulators of the two output
+//     rows of the entry's group (the y pass; group loops are unrolled, so accumulator indices are
+//     compile-time).  All 49 bins x 4 channels of a thread stay in registers;
 //   * epilogue: accumulators -> [256 x 49] shared tile (bank-conflict-free through a per-lane
-//     channel rotation) -> one contiguous 50 KB block of the NCHW output with streaming stores;
-//     optional fused channel mean as in roi_align_fwd_sep.
+//     channel rotation) -> ONE cp.async.bulk store of the contiguous 50 KB block of the NCHW output
+//     (evict-first), which drains while the consumers are in the next RoI; optional fused channel
+//     mean as in roi_align_fwd_sep.
 // Bilinear interpolation is separable, bin = 1/4 * sum_y sum_x wy * wx * f(y, x); the 1/4 is folded
 // into the row weights (exact: a power of two).  The result differs from the reference's
-// summation order by fp32 reassociation only (<= 1e-5 relative, tests/test_gpu_roi_align.py).
+// summation order by fp32 reassociation only (<= 1e-5 relative, tests/test_gpu_roi_align_rows.py);
+// the table / ring-placement algorithm is also checked on the CPU (scripts/emulate_rows_tables.py).
+// Measured steps and dead ends (one producer warp doing everything: 0.77 ms; fixed 28 KB slots;
+// unconditional 4-column loads; 28 consumer warps with 2 channels each; L2 evict-last loads;
+// spatially sorted RoIs): DESIGN.md, "RoIAlign forward".
 #include <cstddef>
 
 #include "roi_align_fwd.cuh"
@@ -42,11 +52,9 @@ constexpr int kRingBytes = kRingPx * kPxBytes;
 constexpr int kNBar = 16;                        // ring entries in flight, at most (barrier pairs)
 constexpr int kHist = 64;                        // placement history the planner keeps (> kNBar + kMaxList)
 constexpr int kTabs = 4;                         // RoI tables in flight
-constexpr int kWarpsPerBin = kRC / 4 / 32;       // 2
-constexpr int kConsWarps = kP * kWarpsPerBin;    // 14
-constexpr int kConsThreads = kConsWarps * 32;    // 448
-constexpr int kPlanWarp = kConsWarps;            // builds the RoI tables, kTabs RoIs ahead
-constexpr int kCopyWarp0 = kConsWarps + 1;       // first of the warps that issue the bulk copies
+// consumers: thread = (kV channels, output column pw); kV = 4: 14 warps, kV = 2: 28 warps
+constexpr int cons_warps(int v) { return kP * (kRC / v / 32); }
+constexpr int kPlanWarps = 2;  // planner warps, alternating RoIs (one warp's ~900 instructions per RoI bounded the kernel)
 constexpr int kTileFloats = kRC * kBins;
 
 // A ring entry = one copy of a tap row, feeding output rows b and b + 1 with weights w0, w1 (x 1/4).
@@ -124,7 +132,15 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
-__device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 1, %0;" ::"n"(kConsThreads) : "memory"); }
+template <int kThreads>
+__device__ __forceinline__ void bar_consumers() {
+  asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
+}
+__device__ __forceinline__ float2 lds_v2(uint32_t a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
 
 struct RoiPlace {
   int level, batch, H, W;
@@ -136,16 +152,17 @@ struct __align__(16) PlanScratch {
   float wy[kMaxList][8];  // weight (x 1/4) of list row i for output row ph
   int rowy[kMaxList];     // feature row of list entry i
   int colx[kMaxList];     // feature column of list entry j
-  uint32_t hist_place[kHist], hist_size[kHist];  // ring placement of the last kHist entries (pixels)
 };
-
-struct RingPlanner {
-  uint32_t g0;    // ring entries of the RoIs planned so far
+// ring placement state, handed from planner warp to planner warp with the placement turn
+struct __align__(16) RingState {
+  uint32_t g0;    // ring entries of the RoIs placed so far
   uint32_t head;  // next free pixel of the ring
+  uint32_t pad[2];
+  uint32_t hist_place[kHist], hist_size[kHist];  // placement of the last kHist entries (pixels)
 };
 
 __device__ __forceinline__ RoiPlace build_rows_tab(const LevelTable& lt, const float* __restrict__ rois, long long r,
-                                                   RoiTab* tb, int lane, RingPlanner& rp, PlanScratch* sc) {
+                                                   RoiTab* tb, int lane, PlanScratch* sc) {
   const RoiHeader h = load_roi(rois, r, lt);
   RoiPlace pl;
   pl.level = h.level;
@@ -294,39 +311,6 @@ __device__ __forceinline__ RoiPlace build_rows_tab(const LevelTable& lt, const f
       if (lane == 0) tb->gend[b] = nent;
     }
   }
-  // ring placement: the entries of a RoI all span ncols pixels and are laid one after the other,
-  // wrapping to the start of the ring when the next one would not fit; an entry's copy depends on the
-  // newest earlier entry whose bytes it overwrites (found in the placement history) and on the
-  // entry that last used its barrier pair
-  {
-    const uint32_t s = (uint32_t)ncols;  // >= 1
-    const uint32_t k0 = ((uint32_t)kRingPx - rp.head) / s, kfit = (uint32_t)kRingPx / s;
-    const uint32_t i = (uint32_t)lane;
-    const uint32_t place = i < k0 ? rp.head + i * s : ((i - k0) % kfit) * s;
-    const uint32_t g = rp.g0 + i;
-    if (lane < nent) {
-      sc->hist_place[g % kHist] = place;
-      sc->hist_size[g % kHist] = s;
-    }
-    __syncwarp();
-    if (lane < nent) {
-      uint32_t dep = g >= (uint32_t)kNBar ? g - (uint32_t)kNBar + 1u : 0u;
-#pragma unroll 5
-      for (uint32_t d = 1; d < (uint32_t)kNBar; ++d) {
-        if (d > g) break;
-        const uint32_t e = g - d;
-        const uint32_t pe = sc->hist_place[e % kHist], se = sc->hist_size[e % kHist];
-        if (pe < place + s && place < pe + se) {
-          dep = dep > e + 1u ? dep : e + 1u;
-          break;  // older overlapping entries only give smaller values
-        }
-      }
-      tb->ent[lane].place = place * (uint32_t)kPxBytes;
-      tb->ent[lane].dep = dep;
-    }
-    if (nent > 0) rp.head = __shfl_sync(0xffffffffu, place, nent - 1) + s;
-    rp.g0 += (uint32_t)nent;
-  }
   // runs of consecutive tapped columns: one bulk copy each
   {
     const int x = lane < ncols ? sc->colx[lane] : 0;
@@ -353,28 +337,84 @@ __device__ __forceinline__ RoiPlace build_rows_tab(const LevelTable& lt, const f
   return pl;
 }
 
+// Ring placement of the entries of one RoI (the planner warp that holds the placement turn): the
+// entries all span ncols pixels and are laid one after the other, wrapping to the start of the ring
+// when the next one would not fit; an entry's copy depends on the newest earlier entry whose bytes it
+// overwrites (found in the placement history) and on the entry that last used its barrier pair.
+__device__ __forceinline__ void place_rows(RoiTab* tb, int lane, RingState* rs) {
+  const int nent = tb->nent;
+  if (nent == 0) return;
+  const uint32_t s = (uint32_t)tb->ncols;  // >= 1
+  const uint32_t g0 = rs->g0, head = rs->head;
+  // small non-negative integers: floor((a + 0.5) / s) through the fp32 reciprocal is exact
+  const float inv = __frcp_rn((float)s);
+  const uint32_t k0 = (uint32_t)(((float)(kRingPx - (int)head) + 0.5f) * inv);
+  const uint32_t kfit = (uint32_t)(((float)kRingPx + 0.5f) * inv);
+  const uint32_t i = (uint32_t)lane;
+  uint32_t j = i - k0;
+  if (i >= k0)
+    while (j >= kfit) j -= kfit;
+  const uint32_t place = i < k0 ? head + i * s : j * s;
+  const uint32_t g = g0 + i;
+  __syncwarp();  // everyone has read g0 / head
+  if (lane < nent) {
+    rs->hist_place[g % kHist] = place;
+    rs->hist_size[g % kHist] = s;
+  }
+  __syncwarp();
+  if (lane < nent) {
+    uint32_t dep = g >= (uint32_t)kNBar ? g - (uint32_t)kNBar + 1u : 0u;
+#pragma unroll 5
+    for (uint32_t d = 1; d < (uint32_t)kNBar; ++d) {
+      if (d > g) break;
+      const uint32_t e = g - d;
+      const uint32_t pe = rs->hist_place[e % kHist], se = rs->hist_size[e % kHist];
+      if (pe < place + s && place < pe + se) {
+        dep = dep > e + 1u ? dep : e + 1u;
+        break;  // older overlapping entries only give smaller values
+      }
+    }
+    tb->ent[lane].place = place * (uint32_t)kPxBytes;
+    tb->ent[lane].dep = dep;
+  }
+  if (lane == nent - 1) {
+    rs->head = place + s;
+    rs->g0 = g0 + (uint32_t)nent;
+  }
+}
+
 // kCopyWarps: warps issuing the bulk copies (ring entry g belongs to warp g % kCopyWarps -- a single
 // warp's dependent instruction stream, ~40 instructions per entry, was what bounded the first version);
 // kProbe != 0: consumers skip the arithmetic (copy-engine throughput probe)
-template <int kCopyWarps, int kProbe>
-__global__ void __launch_bounds__(kConsThreads + 32 + 32 * kCopyWarps, 1)
+template <int kCopyWarps, int kV, int kProbe>
+__global__ void __launch_bounds__(32 * cons_warps(kV) + 32 * kPlanWarps + 32 * kCopyWarps, 1)
 roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, long long n_rois, float* __restrict__ out,
                    float* __restrict__ out_mean, int32_t* __restrict__ out_levels) {
   // (no integer round trip on this pointer: the compiler must keep seeing shared-space addresses,
   // or every access below turns into a generic LD.E / ST.E)
   extern __shared__ __align__(128) unsigned char smem_dyn[];
   __shared__ __align__(128) uint64_t full_bar[kNBar], empty_bar[kNBar], tab_full[kTabs], tab_empty[kTabs];
-  __shared__ PlanScratch plan_scratch;
+  __shared__ PlanScratch plan_scratch[kPlanWarps];
+  __shared__ RingState ring_state;
+  __shared__ __align__(8) uint64_t place_turn[kPlanWarps];
   unsigned char* ring = smem_dyn;
   float* tile = reinterpret_cast<float*>(smem_dyn + (size_t)kRingBytes);
   RoiTab* tabs = reinterpret_cast<RoiTab*>(tile + kTileFloats);
 
+  constexpr int kWarpsPerBin = kRC / kV / 32;
+  constexpr int kConsWarps = cons_warps(kV), kConsThreads = 32 * kConsWarps;
+  constexpr int kPlanWarp0 = kConsWarps;               // first of the warps that build the RoI tables
+  constexpr int kCopyWarp0 = kConsWarps + kPlanWarps;  // first of the warps that issue the bulk copies
+  constexpr int kNP = kV / 2;                 // channel pairs per thread
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s < kNBar; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], kConsWarps);
     }
+    for (int s = 0; s < kPlanWarps; ++s) mbar_init(&place_turn[s], 1);
+    ring_state.g0 = 0;
+    ring_state.head = 0;
     for (int s = 0; s < kTabs; ++s) {
       mbar_init(&tab_full[s], 1);
       mbar_init(&tab_empty[s], kConsWarps + kCopyWarps);  // every reader of a table
@@ -383,19 +423,27 @@ roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, long lon
   }
   __syncthreads();
 
-  if (warp == kPlanWarp) {
-    // ------------------------------- planner: RoI tables ---------------------------------
-    RingPlanner rp;
-    rp.g0 = 0;
-    rp.head = 0;
-    int n = 0;
-    for (long long r = blockIdx.x; r < n_rois; r += gridDim.x, ++n) {
+  if (warp >= kPlanWarp0 && warp < kCopyWarp0) {
+    // ------------------------------- planners: RoI tables --------------------------------
+    // planner p builds the tables of RoIs n = p, p + kPlanWarps, ...; only the ring placement is
+    // sequential across RoIs: it is done holding the placement turn, passed round-robin
+    const int p = warp - kPlanWarp0;
+    int n = p, k = 0;
+    for (long long r = blockIdx.x + (long long)p * gridDim.x; r < n_rois;
+         r += (long long)kPlanWarps * gridDim.x, n += kPlanWarps, ++k) {
       const int ti = n % kTabs;
       mbar_wait(&tab_empty[ti], (uint32_t)(((n / kTabs) & 1) ^ 1));  // (a fresh barrier passes)
-      const RoiPlace pl = build_rows_tab(lt, rois, r, tabs + ti, lane, rp, &plan_scratch);
+      const RoiPlace pl = build_rows_tab(lt, rois, r, tabs + ti, lane, &plan_scratch[p]);
       if (lane == 0 && out_levels) out_levels[r] = pl.level;
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tab_full[ti]);
+      // my turn: after planner p - 1 placed RoI n - 1 (planner 0's first turn is free)
+      mbar_wait(&place_turn[p], (uint32_t)((k & 1) ^ (p == 0 ? 1 : 0)));
+      place_rows(tabs + ti, lane, &ring_state);
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&place_turn[(p + 1) % kPlanWarps]);
+        mbar_arrive(&tab_full[ti]);
+      }
     }
     return;
   }
@@ -443,10 +491,10 @@ roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, long lon
   // --------------------------------- consumers --------------------------------------------
   const int pw = warp / kWarpsPerBin;
   const int q = (warp % kWarpsPerBin) * 32 + lane;
-  const int rot = (lane >> 3) & 3;
+  const int rot = kV == 4 ? (lane >> 3) & 3 : (lane >> 4) & 1;
   // 32-bit shared addresses, pinned in registers (ptxas otherwise re-derives them from the CTA's
   // shared window at every use)
-  uint32_t ring_a = smem_u32(ring) + q * 16, full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
+  uint32_t ring_a = smem_u32(ring) + q * (4 * kV), full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
   uint32_t tabs_a = smem_u32(tabs);
   asm volatile("" : "+r"(ring_a), "+r"(full_a), "+r"(empty_a), "+r"(tabs_a));
   const uint64_t store_policy = policy_evict_first();
@@ -465,12 +513,25 @@ roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, long lon
     const uint32_t c0 = ring_a + cxv.x, c1 = ring_a + cxv.y, c2 = ring_a + cxv.z, c3 = ring_a + cxv.w;
     const float2 wx0 = make_float2(wxv.x, wxv.x), wx1 = make_float2(wxv.y, wxv.y), wx2 = make_float2(wxv.z, wxv.z),
                  wx3 = make_float2(wxv.w, wxv.w);
-    float2 alo[kP], ahi[kP];
+    float2 acc2[kP][kNP];  // [output row][channel pair]
 #pragma unroll
-    for (int ph = 0; ph < kP; ++ph) alo[ph] = ahi[ph] = make_float2(0.f, 0.f);
-    V4 v0, v1, v2, v3;
-    v0.lo = v0.hi = make_float2(0.f, 0.f);
-    v1 = v2 = v3 = v0;
+    for (int ph = 0; ph < kP; ++ph)
+#pragma unroll
+      for (int c = 0; c < kNP; ++c) acc2[ph][c] = make_float2(0.f, 0.f);
+    float2 v[4][kNP];  // [tap column][channel pair]
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int c = 0; c < kNP; ++c) v[k][c] = make_float2(0.f, 0.f);
+    auto lds_col = [&](int k, uint32_t a) {
+      if (kV == 4) {
+        const V4 t = lds_v4(a);
+        v[k][0] = t.lo;
+        v[k][kNP - 1] = t.hi;
+      } else {
+        v[k][0] = lds_v2(a);
+      }
+    };
     // the tap columns of bin pw of the next ring entry -> registers
     auto load_row = [&](uint32_t off) {
       const uint32_t bi = g % kNBar;
@@ -478,10 +539,10 @@ roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, long lon
       if (kProbe == 0) {
         // (loading all four columns unconditionally -- unused ones repeat the first with weight 0 --
         // was measured 15 % slower: shared-memory wavefronts matter more than the two branches)
-        v0 = lds_v4(c0 + off);
-        v1 = lds_v4(c1 + off);
-        if (nk > 2) v2 = lds_v4(c2 + off);
-        if (nk > 3) v3 = lds_v4(c3 + off);
+        lds_col(0, c0 + off);
+        lds_col(1, c1 + off);
+        if (nk > 2) lds_col(2, c2 + off);
+        if (nk > 3) lds_col(3, c3 + off);
       }
       ++g;
     };
@@ -492,21 +553,25 @@ roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, long lon
     for (int b = 0; b < kP; ++b) {
       const uint32_t end_a = tb_a + (uint32_t)offsetof(RoiTab, ent) + 16u * (uint32_t)lds_i32(tb_a + (uint32_t)offsetof(RoiTab, gend) + 4u * b);
       for (; ent_a < end_a; ent_a += 16) {
-        // x pass: the tap columns reduced to one value per channel
         const float2 w = lds_f2(ent_a);
         const uint32_t next_off = (uint32_t)lds_i32(ent_a + 16u + 8u);  // (past the last entry: unused)
-        float2 ulo = make_float2(0.f, 0.f), uhi = ulo;
+        // x pass: the tap columns reduced to one value per channel
+        float2 u[kNP];
+#pragma unroll
+        for (int c = 0; c < kNP; ++c) u[c] = make_float2(0.f, 0.f);
         if (kProbe == 0) {
-          ulo = __fmul2_rn(wx0, v0.lo), uhi = __fmul2_rn(wx0, v0.hi);
-          ulo = __ffma2_rn(wx1, v1.lo, ulo);
-          uhi = __ffma2_rn(wx1, v1.hi, uhi);
+#pragma unroll
+          for (int c = 0; c < kNP; ++c) {
+            u[c] = __fmul2_rn(wx0, v[0][c]);
+            u[c] = __ffma2_rn(wx1, v[1][c], u[c]);
+          }
           if (nk > 2) {
-            ulo = __ffma2_rn(wx2, v2.lo, ulo);
-            uhi = __ffma2_rn(wx2, v2.hi, uhi);
+#pragma unroll
+            for (int c = 0; c < kNP; ++c) u[c] = __ffma2_rn(wx2, v[2][c], u[c]);
           }
           if (nk > 3) {
-            ulo = __ffma2_rn(wx3, v3.lo, ulo);
-            uhi = __ffma2_rn(wx3, v3.hi, uhi);
+#pragma unroll
+            for (int c = 0; c < kNP; ++c) u[c] = __ffma2_rn(wx3, v[3][c], u[c]);
           }
         }
         // this entry has been read: give it back, then fetch the next row while this one is accumulated
@@ -516,60 +581,69 @@ roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, long lon
         if (ent_a < ent_last) load_row(next_off);
         // y pass
         const float2 w0 = make_float2(w.x, w.x);
-        alo[b] = __ffma2_rn(w0, ulo, alo[b]);
-        ahi[b] = __ffma2_rn(w0, uhi, ahi[b]);
+#pragma unroll
+        for (int c = 0; c < kNP; ++c) acc2[b][c] = __ffma2_rn(w0, u[c], acc2[b][c]);
         if (b + 1 < kP) {
           const float2 w1 = make_float2(w.y, w.y);
-          alo[b + 1] = __ffma2_rn(w1, ulo, alo[b + 1]);
-          ahi[b + 1] = __ffma2_rn(w1, uhi, ahi[b + 1]);
+#pragma unroll
+          for (int c = 0; c < kNP; ++c) acc2[b + 1][c] = __ffma2_rn(w1, u[c], acc2[b + 1][c]);
         }
       }
     }
-    float4 acc[kP];
-#pragma unroll
-    for (int ph = 0; ph < kP; ++ph) acc[ph] = make_float4(alo[ph].x, alo[ph].y, ahi[ph].x, ahi[ph].y);
     // the tables of this RoI are no longer needed
     __syncwarp();
     if (lane == 0) mbar_arrive(&tab_empty[ti]);
 
     // ---- epilogue: registers -> [256 x 49] tile -> one contiguous block of the output -------
     if (tid == 0) bulk_wait_read();  // the bulk store of the previous RoI has read the tile
-    bar_consumers();
+    bar_consumers<kConsThreads>();
     {
-      // lane groups of 8 write different channels of their quad in one instruction (rotation by
-      // lane / 8): 32 lanes then hit 32 different banks (quad stride 196 = 4 mod 32, channel 49 = 17)
-      float* t0 = tile + (4 * q) * kBins + pw;
-      float* tc[4];
+      // lane groups write different channels of their thread's kV in one instruction (rotation by
+      // lane / 8 for kV = 4, lane / 16 for kV = 2): the 32 lanes then hit 32 different banks
+      // (thread stride 49 * kV floats = kV mod 32, channel stride 49 = 17 mod 32)
+      float* t0 = tile + (kV * q) * kBins + pw;
+      float* tc[kV];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) tc[j] = t0 + ((j + rot) & 3) * kBins;
+      for (int j = 0; j < kV; ++j) tc[j] = t0 + ((j + rot) % kV) * kBins;
 #pragma unroll
       for (int ph = 0; ph < kP; ++ph) {
-        float a = acc[ph].x, b = acc[ph].y, c = acc[ph].z, d = acc[ph].w;
-        if (rot & 1) {
-          const float t = a;
-          a = b;
-          b = c;
-          c = d;
-          d = t;
+        if (kV == 4) {
+          float a = acc2[ph][0].x, b = acc2[ph][0].y, c = acc2[ph][kNP - 1].x, d = acc2[ph][kNP - 1].y;
+          if (rot & 1) {
+            const float t = a;
+            a = b;
+            b = c;
+            c = d;
+            d = t;
+          }
+          if (rot & 2) {
+            float t = a;
+            a = c;
+            c = t;
+            t = b;
+            b = d;
+            d = t;
+          }
+          tc[0][ph * kP] = a;
+          tc[1][ph * kP] = b;
+          tc[kV - 2][ph * kP] = c;
+          tc[kV - 1][ph * kP] = d;
+        } else {
+          float a = acc2[ph][0].x, b = acc2[ph][0].y;
+          if (rot & 1) {
+            const float t = a;
+            a = b;
+            b = t;
+          }
+          tc[0][ph * kP] = a;
+          tc[1][ph * kP] = b;
         }
-        if (rot & 2) {
-          float t = a;
-          a = c;
-          c = t;
-          t = b;
-          b = d;
-          d = t;
-        }
-        tc[0][ph * kP] = a;
-        tc[1][ph * kP] = b;
-        tc[2][ph * kP] = c;
-        tc[3][ph * kP] = d;
       }
     }
     // one contiguous 50 KB block of the NCHW output: a single bulk store (TMA) drains the tile while
     // the consumers are already in the next RoI's rows
     fence_proxy_async();  // this thread's tile writes -> visible to the async proxy
-    bar_consumers();
+    bar_consumers<kConsThreads>();
     {
       if (tid == 0) bulk_s2g(out + (size_t)r * kTileFloats, smem_u32(tile), kTileFloats * 4, store_policy);
       if (out_mean && tid < kRC) {
@@ -594,21 +668,21 @@ bool rows_kernel_applies(const LevelTable& lt, int C, int PH, int PW) {
 // Preconditions (checked by the caller): NHWC, sampling_ratio 2; rows_kernel_applies().
 int launch_forward_rows(const LevelTable& lt, int C, const float* rois, int64_t n_rois, float* out, float* out_mean,
                         int32_t* out_levels, int variant, cudaStream_t st) {
-  static_assert(kTileFloats / 4 % kConsThreads == 0, "copy-out assumes whole passes");
   B200_REQUIRE(C == kRC, "roi_align rows kernel: %d channels", C);
   const int64_t grid = n_rois < sm_count() ? n_rois : sm_count();
-#define B200_ROWS(CW, PROBE)                                                                                      \
+#define B200_ROWS(CW, V, PROBE)                                                                                   \
   do {                                                                                                            \
     static SmemHighWater hw;                                                                                      \
-    int rc = ensure_dynamic_smem(roi_align_fwd_rows<CW, PROBE>, kRowsSmem, &hw, "roi_align rows: smem");          \
+    int rc = ensure_dynamic_smem(roi_align_fwd_rows<CW, V, PROBE>, kRowsSmem, &hw, "roi_align rows: smem");       \
     if (rc != B200_OK) return rc;                                                                                 \
-    roi_align_fwd_rows<CW, PROBE><<<(unsigned)grid, kConsThreads + 32 + 32 * CW, kRowsSmem, st>>>(                \
+    roi_align_fwd_rows<CW, V, PROBE><<<(unsigned)grid, 32 * cons_warps(V) + 32 * kPlanWarps + 32 * CW, kRowsSmem, st>>>(       \
         lt, rois, (long long)n_rois, out, out_mean, out_levels);                                                  \
   } while (0)
-  // variant (tuning hook of b200_debug_set): bit 5 = four copy warps instead of two, bit 6 = copy-engine probe
-  if (variant & 64) B200_ROWS(2, 1);
-  else if (variant & 32) B200_ROWS(4, 0);
-  else B200_ROWS(2, 0);
+  // variant (tuning hook of b200_debug_set): bit 5 = two channels per consumer thread (28 consumer warps),
+  // bit 6 = copy-engine probe (no arithmetic)
+  if (variant & 64) B200_ROWS(2, 4, 1);
+  else if (variant & 32) B200_ROWS(2, 2, 0);
+  else B200_ROWS(2, 4, 0);
 #undef B200_ROWS
   B200_CHECK_LAUNCH("roi_align_fwd_rows");
   return B200_OK;

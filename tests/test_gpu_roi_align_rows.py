@@ -46,14 +46,19 @@ EDGE = np.array([
 ], dtype=np.float32)
 
 
+# 0: four channels per consumer thread (14 consumer warps); 32: two channels (28 consumer warps)
+LAYOUTS = [0, 32]
+
+
 @pytest.mark.timeout(120)
-def test_rows_kernel_matches_oracle_multilevel():
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_rows_kernel_matches_oracle_multilevel(layout):
     rng = np.random.default_rng(2601)
     b, n = 2, 150
     feats = _pyramid(rng, b, 256)
     rois = np.concatenate([synth.make_rois(rng, n, b, smin=6.0), EDGE]).astype(np.float32)
     want, wl = oracle.pooler_forward([f.cpu().contiguous().numpy() for f in feats], rois, synth.FPN_SCALES, 7, 7, 2)
-    got, lv = _fwd(feats, synth.FPN_SCALES, torch.from_numpy(rois).cuda(), ROWS, want_levels=True)
+    got, lv = _fwd(feats, synth.FPN_SCALES, torch.from_numpy(rois).cuda(), ROWS | layout, want_levels=True)
     got = got.cpu().numpy()
     assert np.array_equal(lv.cpu().numpy(), wl)
     np.testing.assert_allclose(got, want, rtol=RTOL, atol=1e-6)
@@ -66,20 +71,22 @@ def test_rows_kernel_matches_oracle_multilevel():
 
 
 @pytest.mark.timeout(120)
-def test_rows_kernel_single_level_sparse_taps():
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_rows_kernel_single_level_sparse_taps(layout):
     """One level, RoIs much wider than 28 feature pixels: the tapped columns split into many runs."""
     rng = np.random.default_rng(2602)
     x = torch.from_numpy(rng.standard_normal((2, 256, 100, 168)).astype(np.float32)).cuda() \
         .contiguous(memory_format=torch.channels_last)
     rois = synth.make_rois(rng, 80, 2, smin=150.0, smax=1300.0, degenerate=0.0)
     want = oracle.roi_align_forward(x.cpu().contiguous().numpy(), rois, 1 / 8, 7, 7, 2)
-    got, _ = _fwd([x], (1 / 8,), torch.from_numpy(rois).cuda(), ROWS)
+    got, _ = _fwd([x], (1 / 8,), torch.from_numpy(rois).cuda(), ROWS | layout)
     np.testing.assert_allclose(got.cpu().numpy(), want, rtol=RTOL, atol=1e-6)
 
 
 @pytest.mark.timeout(120)
 @pytest.mark.parametrize("n", [1, 3, 149, 700])
-def test_rows_kernel_small_grids_and_mean(n):
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_rows_kernel_small_grids_and_mean(n, layout):
     """Fewer RoIs than SMs, one more than a multiple, several per CTA; fused channel mean; run-to-run
     bit-identical (no atomics, fixed summation order)."""
     rng = np.random.default_rng(2603 + n)
@@ -87,10 +94,10 @@ def test_rows_kernel_small_grids_and_mean(n):
     rois = torch.from_numpy(synth.make_rois(rng, n, 1, 672, 400, smin=8.0, smax=600.0)).cuda()
     want, _ = oracle.pooler_forward([f.cpu().contiguous().numpy() for f in feats], rois.cpu().numpy(),
                                     synth.FPN_SCALES, 7, 7, 2)
-    pooled, mean = _fwd(feats, synth.FPN_SCALES, rois, ROWS, mean=True)
+    pooled, mean = _fwd(feats, synth.FPN_SCALES, rois, ROWS | layout, mean=True)
     np.testing.assert_allclose(pooled.cpu().numpy(), want, rtol=RTOL, atol=1e-6)
     assert torch.allclose(mean, pooled.mean(dim=(2, 3)), rtol=1e-5, atol=1e-6)
-    again, _ = _fwd(feats, synth.FPN_SCALES, rois, ROWS)
+    again, _ = _fwd(feats, synth.FPN_SCALES, rois, ROWS | layout)
     assert torch.equal(again, pooled)
 
 
