@@ -6,6 +6,12 @@ Same parameters (`emb_pred`, `bbox_pred`), same `set_class_embeddings`, same
 `einsum('pe,ce->pc', cls_emb, cls_score)` (:67) runs on the tcgen05 kernel; in eval mode the
 row softmax that PostProcessor would compute next (box_head/inference.py:62) is produced by
 the same launch and handed over as `cls_logit.b200_probs`.
+
+`fold_projection()` (inference only): the projection GEMM is folded into the class
+matrix, logits = x . (E W)^T + E b, so the [R, in] x [in, emb_dim] product (30x the FLOPs of the
+scoring at 66 classes) disappears and the pooled features go straight into the tensor-core kernel:
+E W is rounded to bf16 once; the bias term E b rides along as two extra K columns (bf16 hi + lo
+parts against ones in the activations).  Same tolerance bars as the unfolded path (2e-2 / 99.9 %).
 """
 import torch
 from torch import nn
@@ -52,6 +58,31 @@ class FastRCNNPredictor(nn.Module):
         nn.init.constant_(self.bbox_pred.bias, 0)
         self.score_thresh = float(_get(config, "MODEL.ROI_HEADS.SCORE_THRESH", 0.05))
         self._cls_bf16 = None
+        self._fold = False
+        self._folded = None  # (key, class matrix [C, in + 8] bf16)
+
+    def fold_projection(self, enable=True):
+        """Inference: score pooled features against E.W (+ E.b) directly (module docstring)."""
+        if enable and not self.embedding_based:
+            raise ValueError("fold_projection needs the embedding-based predictor")
+        self._fold = bool(enable)
+        self._folded = None
+        return self
+
+    def _folded_matrix(self):
+        w, b, e = self.emb_pred.weight, self.emb_pred.bias, self.cls_score
+        key = (w._version, b._version, e._version, e.data_ptr(), e.shape, w.device)
+        if self._folded is None or self._folded[0] != key:
+            with torch.no_grad():
+                e32 = e.detach().to(w.device, torch.float32)
+                ew = e32 @ w.detach().float()                      # [C, in]
+                eb = e32 @ b.detach().float()                      # [C]
+                hi = eb.to(torch.bfloat16)
+                lo = (eb - hi.float()).to(torch.bfloat16)
+                pad = torch.zeros((e32.shape[0], 6), dtype=torch.bfloat16, device=w.device)
+                mat = torch.cat([ew.to(torch.bfloat16), hi[:, None], lo[:, None], pad], dim=1).contiguous()
+            self._folded = (key, mat)
+        return self._folded[1]
 
     def set_class_embeddings(self, embs):
         """embs [C, emb_dim]; row 0 is the all-zero background row (reference :84-92)."""
@@ -70,12 +101,23 @@ class FastRCNNPredictor(nn.Module):
         if x.dim() == 4:
             x = self.avgpool(x)
         x = x.view(x.size(0), -1)
-        if self.embedding_based:
+        if self.embedding_based and self._fold and not self.training and not (torch.is_grad_enabled() and x.requires_grad):
+            E = self._folded_matrix()
+            k = x.shape[1]
+            a = torch.empty((x.shape[0], k + 8), dtype=torch.bfloat16, device=x.device)
+            a[:, :k] = x
+            a[:, k:k + 2] = 1      # against the hi / lo parts of E.b
+            a[:, k + 2:] = 0
+            out = embed_match_softmax(a, E, self.score_thresh, want_probs=True, want_logits=True)
+            cls_logit = out["logits"]
+            cls_logit.b200_probs = out["probs"]
+            cls_logit.b200_top_label = out["top_label"]
+            cls_logit.b200_top_prob = out["top_prob"]
+        elif self.embedding_based:
             cls_emb = self.emb_pred(x)
             E = self._class_matrix()
-            if not cls_emb.is_cuda:
-                cls_logit = torch.einsum("pe,ce->pc", cls_emb, self.cls_score)
-            elif torch.is_grad_enabled() and cls_emb.requires_grad:
+            # (no CPU path: embed_logits / embed_match_softmax raise on CPU tensors)
+            if torch.is_grad_enabled() and cls_emb.requires_grad:
                 cls_logit = embed_logits(cls_emb, E)
             else:
                 out = embed_match_softmax(cls_emb, E, self.score_thresh, want_probs=True, want_logits=True)

@@ -68,6 +68,14 @@ def test_cpu_tensors_are_rejected_everywhere():
         embed_match_softmax(torch.zeros(4, 8), torch.zeros(2, 8))
     with pytest.raises(RuntimeError):
         Pooler((7, 7), (0.25, 0.125), 2)([x, x[:, :, ::2, ::2]], [BoxList(rois[:, 1:], (32, 32))])
+    # the embedding predictor scores through the tensor-core kernel only: no einsum on the CPU
+    from cvpr22_cross_modal_pseudo_labeling_b200.modeling import FastRCNNPredictor
+    pred = FastRCNNPredictor({"MODEL": {"ROI_BOX_HEAD": {"EMB_DIM": 8}}}, 16).eval()
+    pred.set_class_embeddings(torch.zeros(3, 8))
+    with pytest.raises(RuntimeError), torch.no_grad():
+        pred(torch.zeros(4, 16))
+    with pytest.raises(RuntimeError):
+        pred(torch.zeros(4, 16))
 
 
 def test_boxlist_semantics():

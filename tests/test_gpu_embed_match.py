@@ -114,3 +114,51 @@ def test_bad_arguments():
         embed_match_softmax(torch.zeros((4, 12), device="cuda"), torch.zeros((2, 12), device="cuda"))  # dim % 8
     out = embed_match_softmax(torch.zeros((4, 8), device="cuda"), torch.zeros((513, 8), device="cuda"))
     assert torch.allclose(out["probs"], torch.full((4, 513), 1.0 / 513, device="cuda"))   # wide path, uniform
+
+
+def test_predictor_folded_projection():
+    """SURVEY 8f-2, inference form: FastRCNNPredictor.fold_projection() scores the pooled features
+    against E.W (+ E.b as two extra K columns) in one tensor-core launch; within the 2e-2 / 99.9 % bars of
+    the fp32 chain (avgpool -> emb_pred -> einsum -> softmax, roi_box_predictors.py:62-67 and
+    box_head/inference.py:62), and of the unfolded module."""
+    from types import SimpleNamespace as NS
+    from cvpr22_cross_modal_pseudo_labeling_b200.modeling import FastRCNNPredictor
+    g = torch.Generator().manual_seed(77)
+    r, k, d, c = 1500, 2048, 768, 66
+    cfg = NS(MODEL=NS(ROI_BOX_HEAD=NS(EMBEDDING_BASED=True, EMB_DIM=d, FREEZE_EMB_PRED=False),
+                      CLS_AGNOSTIC_BBOX_REG=True, ROI_HEADS=NS(SCORE_THRESH=0.05)))
+    pred = FastRCNNPredictor(cfg, k).cuda().eval()
+    with torch.no_grad():
+        pred.emb_pred.weight.copy_(torch.randn((d, k), generator=g) * (1.0 / k ** 0.5))
+        pred.emb_pred.bias.copy_(torch.randn((d,), generator=g) * 0.2)
+    E = torch.nn.functional.normalize(torch.randn((c, d), generator=g), dim=-1) * 3.0
+    E[0] = 0
+    pred.set_class_embeddings(E.cuda())
+    x = torch.randn((r, k, 1, 1), generator=g).cuda()
+    with torch.no_grad():
+        emb = torch.nn.functional.linear(x.view(r, k).double(), pred.emb_pred.weight.double(), pred.emb_pred.bias.double())
+        want_logits = emb @ E.cuda().double().t()
+        want = torch.softmax(want_logits, -1)
+        plain, reg0 = pred(x)
+        pred.fold_projection()
+        folded, reg1 = pred(x)
+        assert torch.equal(reg0, reg1)
+        # the fold moves the bf16 rounding points (E.W instead of cls_emb and E), so against the UNROUNDED
+        # fp64 chain near-ties may flip: top-1 must agree wherever the winner leads by more than 0.1 in logit
+        top2 = want_logits[:, 1:].topk(2, dim=1).values
+        clear = (top2[:, 0] - top2[:, 1]) > 0.1
+        assert float(clear.double().mean()) > 0.8
+        for got in (plain, folded):
+            assert float((got.b200_probs.double() - want).abs().max()) < 2e-2
+            same = got.b200_probs[:, 1:].argmax(1) == want[:, 1:].argmax(1)
+            assert float(same[clear].double().mean()) >= 0.999 and float(same.double().mean()) >= 0.97
+        assert float((folded.double() - want_logits).abs().max()) < 2e-2 * float(want_logits.abs().max())
+        assert float(folded[:, 0].abs().max()) == 0.0          # the background row stays exactly zero
+        # the cache follows the parameters
+        pred.emb_pred.bias.add_(1.0)
+        again, _ = pred(x)
+        shift = (E.cuda().double().sum(1))[None, :]
+        assert float((again.double() - (want_logits + shift)).abs().max()) < 2e-2 * float((want_logits + shift).abs().max())
+        pred.fold_projection(False)
+        back, _ = pred(x)
+        assert float((back.double() - (want_logits + shift)).abs().max()) < 2e-2 * float((want_logits + shift).abs().max())
