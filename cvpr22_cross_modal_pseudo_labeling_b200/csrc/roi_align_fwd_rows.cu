@@ -30,7 +30,7 @@
 // Bilinear interpolation is separable, bin = 1/4 * sum_y sum_x wy * wx * f(y, x); the 1/4 is folded
 // into the row weights (exact: a power of two).  The result differs from the reference's
 // summation order by fp32 reassociation only (<= 1e-5 relative, tests/test_gpu_roi_align_rows.py);
-// the table / ring-placement algorithm is also checked on the CPU (scripts/emulate_rows_tables.py).
+// the table / ring-placement algorithm is also checked on the CPU (tests/rows_tables_emulation.py).
 // Measured steps and dead ends (one producer warp doing everything: 0.77 ms; fixed 28 KB slots;
 // unconditional 4-column loads; 28 consumer warps with 2 channels each; L2 evict-last loads;
 // spatially sorted RoIs): DESIGN.md, "RoIAlign forward".

@@ -2,9 +2,9 @@
 
 Transcribes build_rows_tab() lane by lane (numpy, fp32) and evaluates the x pass / y pass exactly
 as the consumer threads do, then compares with the C oracle (oracle.pooler_forward).  It checks the
-ALGORITHM (list construction, tap merging, row entries, runs), not the CUDA transcription; the
+ALGORITHM (list construction, tap merging, ring entries and their grouping, runs, ring placement), not the CUDA transcription; the
 GPU parity tests do that.  Test infrastructure only (imports oracle/).
-    python scripts/emulate_rows_tables.py [n_rois]
+    python tests/rows_tables_emulation.py [n_rois]
 """
 import os
 import sys
@@ -119,29 +119,33 @@ def emulate_roi(feats, roi, scales, k_min, k_max, stats):
         for idx, w in taps:
             assert wy[idx, ph] == 0
             wy[idx, ph] = f32(f32(0.25) * w)
+    # ring entries: per list row the output rows it feeds, paired greedily from the lowest one
+    # (b, b + 1); the pairs of all rows ordered by b (the kernel's counting sort is stable in the row)
+    entries = []
+    for i in range(len(rows)):
+        left = {ph for ph in range(P) if wy[i, ph] != 0}
+        for bb in range(P):
+            if bb in left:
+                entries.append((bb, i, wy[i, bb], wy[i, bb + 1] if bb + 1 < P else f32(0)))
+                left.discard(bb)
+                left.discard(bb + 1)
+    entries.sort(key=lambda e: (e[0], e[1]))
+    assert len(entries) <= 28
+    stats["entries"] = stats.get("entries", 0) + len(entries)
+    stats["generic"] += sum(1 for i in range(len(rows)) if sum(1 for e in entries if e[1] == i) > 1)
     acc = np.zeros((P, P, C), np.float32)
-    for i, y in enumerate(rows):
+    for bb, i, w0, w1 in entries:  # the consumers: one ring entry = one copy of tap row i
+        y = rows[i]
         slot = np.zeros((28, C), np.float32)
         for pos, col, ln in runs:
             slot[pos:pos + ln] = f[b, y, col:col + ln]
-        mask = [ph for ph in range(P) if wy[i, ph] != 0]
-        if mask and (mask[-1] - mask[0] + 1) > 2:
-            stats["generic"] += 1
         for pw, taps in enumerate(xbins):
             u = np.zeros(C, np.float32)
             for idx, w in taps:
                 u = (u + w * slot[idx]).astype(np.float32)
-            if not mask:
-                continue
-            blo = mask[0]
-            if mask[-1] - blo + 1 <= 2:
-                acc[blo, pw] += wy[i, blo] * u
-                if blo + 1 < P:
-                    acc[blo + 1, pw] += wy[i, blo + 1] * u
-            else:
-                for ph in range(P):
-                    if wy[i, ph] != 0:
-                        acc[ph, pw] += wy[i, ph] * u
+            acc[bb, pw] += w0 * u
+            if bb + 1 < P:
+                acc[bb + 1, pw] += w1 * u
     return acc.transpose(2, 0, 1), lvl
 
 
@@ -172,8 +176,8 @@ def main():
         assert np.allclose(got, want[i], rtol=1e-5, atol=2e-6), (i, roi, err)
         worst = max(worst, err)
     m = len(rois)
-    print("ok: %d RoIs, worst rel err %.2e; per RoI: rows %.1f cols %.1f runs %.2f; generic rows %d" %
-          (m, worst, stats["rows"] / m, stats["cols"] / m, stats["runs"] / m, stats["generic"]))
+    print("ok: %d RoIs, worst rel err %.2e; per RoI: rows %.1f (ring entries %.1f) cols %.1f runs %.2f; rows copied more than once %d" %
+          (m, worst, stats["rows"] / m, stats["entries"] / m, stats["cols"] / m, stats["runs"] / m, stats["generic"]))
     # single-level pooler with wide RoIs (sparse taps -> many runs)
     f1 = [feats_nchw[1]]
     big = synth.make_rois(rng, 60, B, 672, 400, smin=100, smax=700, degenerate=0.0)
