@@ -53,10 +53,15 @@ def main():
             out_bytes = R * C * res_ * res_ * 4
             algo = pyr_bytes + out_bytes + R * 20
             for exact in (True, False):
-                for pk in (0, 1, 2):
+                # fast math: variant 0 = the default (box 7x7 at 256 channels: the row-streaming kernel),
+                # 16 + v = the separable marching kernel with occupancy variant v
+                for pk in ((0, 1, 2) if exact else (0, 16, 17, 18)):
                     _ext.debug_set(False, exact, pk)
                     med, best = timeit(lambda: _forward(feats, synth.FPN_SCALES, rois, (res_, res_), 2))
-                    key = "fwd_%s_%s_v%d" % (name, "exact" if exact else "fma", pk)
+                    tag = "v%d" % pk if pk < 16 else "sep_v%d" % (pk - 16)
+                    if not exact and pk == 0 and res_ == 7 and C == 256:
+                        tag = "rows"
+                    key = "fwd_%s_%s_%s" % (name, "exact" if exact else "fma", tag)
                     res[key] = dict(ms=med, best_ms=best, GBs=algo / med / 1e6, mroi_s=R / med / 1e3)
                     print(key, res[key], flush=True)
             _ext.debug_set(True, True, 0)
