@@ -118,8 +118,14 @@ def debug_rpn(force_exact=False):
 
 
 def debug_set(force_generic=False, exact=True, variant=0):
-    """Tuning / test hook: select the generic RoIAlign kernel, the FMA variant,
-    or the staged kernel's patch budget."""
+    """Tuning / test hook (not part of the reference-facing ABI): select the generic RoIAlign kernel,
+    the arithmetic of b200_roi_align_forward (exact / FMA), and a kernel variant:
+      bits 0-3  occupancy variants of the marching kernels (1, 2; 8 = one channel chunk per CTA)
+      bit 4     (16) fast math at the FPN box pooler shape: the separable marching kernel instead of
+                the row-streaming kernel
+      bit 5     (32) row-streaming kernel with two channels per consumer thread (28 consumer warps)
+      bit 6     (64) row-streaming kernel without arithmetic (copy-pipeline probe; output is zeros)
+    Process-wide; tests and probes reset it to (False, True, 0)."""
     lib().b200_debug_set(int(force_generic), int(exact), int(variant))
 
 
