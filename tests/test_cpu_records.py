@@ -123,3 +123,45 @@ def test_bad_files_fail_loudly(tmp_path):
         R.save_records(bad, rec[:, :, :7], cnt)
     with pytest.raises(ValueError):
         R.save_records(bad, rec, cnt + 9)
+
+
+_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["REPO_ROOT"])
+from cvpr22_cross_modal_pseudo_labeling_b200 import records as R
+from cvpr22_cross_modal_pseudo_labeling_b200.parallel import all_gather_records, shard_range
+dist.init_process_group("gloo", init_method="env://")
+rank, ws = dist.get_rank(), dist.get_world_size()
+n_img, w_max, out = 7, 5, os.environ["OUT_DIR"]
+g = torch.Generator().manual_seed(99)                 # every rank draws the same full set, keeps its shard
+full = torch.rand((n_img, w_max, 8), generator=g)
+cnt = torch.randint(0, w_max + 1, (n_img,), generator=g, dtype=torch.int32)
+full = full * (torch.arange(w_max)[None, :, None] < cnt[:, None, None])
+lo, hi = shard_range(n_img)
+R.save_records(os.path.join(out, "shard%d.b2pl" % rank), full[lo:hi], cnt[lo:hi], {"rank": rank})
+allr, allc = all_gather_records(full[lo:hi].contiguous(), cnt[lo:hi].contiguous())
+dist.barrier()
+if rank == 0:
+    R.merge_record_files([os.path.join(out, "shard%d.b2pl" % r) for r in range(ws)], os.path.join(out, "all.b2pl"))
+    rec, c, meta = R.load_records(os.path.join(out, "all.b2pl"))
+    assert torch.equal(rec, allr) and torch.equal(c, allc) and torch.equal(rec, full) and torch.equal(c, cnt)
+    assert [m["rank"] for m in meta["shards"]] == list(range(ws))
+dist.barrier(); dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_shard_files_merge_to_what_the_all_gather_returns_gloo(tmp_path):
+    """world_size 2 (gloo): every rank writes its shard file and joins the all-gather; the merged file
+    equals the gathered records -- the wire format and the disk format are the same thing."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, REPO_ROOT=root, OUT_DIR=str(tmp_path), MASTER_ADDR="127.0.0.1", MASTER_PORT="29633",
+               WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
