@@ -123,14 +123,16 @@ seg_scan_kernel(const int32_t* __restrict__ seg_len, long long n, long long capa
     __syncthreads();
     const int carry = carry_s;
     const int incl = carry + s + (warp > 0 ? warp_sum[warp - 1] : 0);
-    if (i < n) seg_off[i] = incl - v;
+    // offsets are clamped to the capacity: on overflow (status[1], raised by the host after the chain) the
+    // NMS / selection kernels that follow still see in-bounds -- truncated or empty -- segments
+    if (i < n) seg_off[i] = (int)min((long long)(incl - v), capacity);
     __syncthreads();
     if (tid == 1023) carry_s = incl;
     __syncthreads();
   }
   if (tid == 0) {
     const int total = carry_s;
-    seg_off[n] = total;
+    seg_off[n] = (int)min((long long)total, capacity);
     status[0] = total;
     status[1] = (long long)total > capacity ? 1 : 0;
   }

@@ -58,19 +58,24 @@ def embed_match_softmax(A, E, score_thresh=0.05, want_probs=True, want_logits=Fa
 
 
 class _EmbedLogits(Function):
-    """cls_logit = cls_emb . E^T with gradient w.r.t. cls_emb (the class matrix is a constant,
-    reference roi_box_predictors.py:84-92)."""
+    """cls_logit = cls_emb . E^T (reference roi_box_predictors.py:67, an einsum that differentiates
+    into both operands).  The gradient w.r.t. cls_emb is always produced; the gradient w.r.t. the class
+    matrix is produced when E requires grad -- in the reference it does once exemplars are loaded:
+    `set_class_embeddings(self.combine_embs(...))` (st_generalized_rcnn.py:173, :372-375) makes E a
+    function of the learnable `lambda_exemplar`."""
 
     @staticmethod
     def forward(ctx, cls_emb, E):
-        ctx.save_for_backward(E)
-        ctx.in_dtype = cls_emb.dtype
+        ctx.save_for_backward(cls_emb, E)
         return embed_match_softmax(cls_emb, E, want_probs=False, want_logits=True, want_top=False)["logits"]
 
     @staticmethod
     def backward(ctx, grad_logits):
-        (E,) = ctx.saved_tensors
-        return (grad_logits.float() @ E.float()).to(ctx.in_dtype), None
+        cls_emb, E = ctx.saved_tensors
+        g = grad_logits.float()
+        g_emb = (g @ E.float()).to(cls_emb.dtype) if ctx.needs_input_grad[0] else None
+        g_E = (g.t() @ cls_emb.float()).to(E.dtype) if ctx.needs_input_grad[1] else None
+        return g_emb, g_E
 
 
 def embed_logits(cls_emb, E):

@@ -57,6 +57,51 @@ def nms_batched(boxes, scores, seg_offsets, thresh, max_keep=-1, max_seg_len=Non
     return keep_idx, keep_cnt
 
 
+_MAX_SEG = 16384  # B200_NMS_MAX_SEG (include/b200det.h): longest segment one b200_nms_batched call takes
+
+
+def _suppressed_by(rest, kept, threshold, chunk=1 << 22):
+    """rest [M,4], kept [K,4] -> bool [M]: IoU(rest_i, kept_j) >= threshold for some j, every operation
+    rounded separately in fp32 in the order of csrc/cpu/nms_cpu.cpp:45-57 (legacy +1 extents)."""
+    out = torch.zeros((rest.size(0),), dtype=torch.bool, device=rest.device)
+    if kept.size(0) == 0 or rest.size(0) == 0:
+        return out
+    ka = (kept[:, 2] - kept[:, 0] + 1) * (kept[:, 3] - kept[:, 1] + 1)
+    step = max(1, chunk // kept.size(0))
+    for o in range(0, rest.size(0), step):
+        r = rest[o:o + step]
+        ra = (r[:, 2] - r[:, 0] + 1) * (r[:, 3] - r[:, 1] + 1)
+        w = (torch.minimum(kept[None, :, 2], r[:, None, 2]) - torch.maximum(kept[None, :, 0], r[:, None, 0]) + 1).clamp_(min=0)
+        h = (torch.minimum(kept[None, :, 3], r[:, None, 3]) - torch.maximum(kept[None, :, 1], r[:, None, 1]) + 1).clamp_(min=0)
+        inter = w * h
+        out[o:o + step] = (inter / (ka[None, :] + ra[:, None] - inter) >= threshold).any(1)
+    return out
+
+
+def _nms_long(dets, scores, threshold):
+    """Segments longer than B200_NMS_MAX_SEG (the reference handles any N): greedy NMS is block-recursive on
+    the score-sorted list -- the kept boxes of the first block do not depend on later boxes, later boxes
+    are first filtered by them, and the survivors are the next problem.  Each block runs through
+    b200_nms_batched; the cross-block filter is elementwise torch in the reference's operation order."""
+    order = torch.sort(scores.float(), descending=True, stable=True).indices   # ties: ascending index
+    boxes = dets.float()[order].contiguous()
+    kept = []
+    while boxes.size(0) > 0:
+        blk = boxes[:_MAX_SEG].contiguous()
+        m = blk.size(0)
+        rank = torch.arange(m, 0, -1, dtype=torch.float32, device=dets.device)  # already sorted: keep that order
+        off = torch.tensor([0, m], dtype=torch.int32, device=dets.device)
+        ki, kc = nms_batched(blk, rank, off, threshold, -1, m)
+        k = ki[: int(kc.item())]
+        kept.append(order[:m][k])
+        rest, rest_order = boxes[m:], order[m:]
+        if rest.size(0) == 0:
+            break
+        alive = ~_suppressed_by(rest, blk[k], threshold)
+        boxes, order = rest[alive].contiguous(), rest_order[alive]
+    return torch.sort(torch.cat(kept)).values
+
+
 def nms(dets, scores, threshold):
     """_C.nms(dets[N,4], scores[N], threshold) -> int64 keep indices, ascending
     (reference csrc/cpu/nms_cpu.cpp:64).  Semantics of the CPU reference (`>=`,
@@ -68,6 +113,8 @@ def nms(dets, scores, threshold):
         # reference returns an empty int64 CPU tensor (csrc/nms.h:17-18); keep the device
         return torch.empty((0,), dtype=torch.int64, device=dets.device)
     n = dets.size(0)
+    if n > _MAX_SEG:
+        return _nms_long(dets, scores, threshold)
     off = torch.tensor([0, n], dtype=torch.int32, device=dets.device)
     keep_idx, keep_cnt = nms_batched(dets, scores, off, threshold, -1, n)
     return keep_idx[: int(keep_cnt.item())]

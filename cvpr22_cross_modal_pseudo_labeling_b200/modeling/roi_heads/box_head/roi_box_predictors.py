@@ -92,10 +92,14 @@ class FastRCNNPredictor(nn.Module):
         self._cls_bf16 = None
 
     def _class_matrix(self):
-        if self._cls_bf16 is None or self._cls_bf16.shape != self.cls_score.shape or \
-                self._cls_bf16.device != self.cls_score.device:
-            self._cls_bf16 = self.cls_score.detach().to(torch.bfloat16).contiguous()
-        return self._cls_bf16
+        """bf16 copy of the class matrix, keyed like _folded_matrix on storage, version, shape and device:
+        the reference also assigns `predictor.cls_score = ...` directly (st_generalized_rcnn.py:194) and
+        may edit it in place, neither of which passes through set_class_embeddings."""
+        e = self.cls_score
+        key = (e.data_ptr(), e._version, tuple(e.shape), e.device)
+        if self._cls_bf16 is None or self._cls_bf16[0] != key:
+            self._cls_bf16 = (key, e.detach().to(torch.bfloat16).contiguous())
+        return self._cls_bf16[1]
 
     def forward(self, x, compute_uncertain=False):
         if x.dim() == 4:
@@ -115,9 +119,12 @@ class FastRCNNPredictor(nn.Module):
             cls_logit.b200_top_prob = out["top_prob"]
         elif self.embedding_based:
             cls_emb = self.emb_pred(x)
-            E = self._class_matrix()
             # (no CPU path: embed_logits / embed_match_softmax raise on CPU tensors)
-            if torch.is_grad_enabled() and cls_emb.requires_grad:
+            e_grad = torch.is_grad_enabled() and self.cls_score.requires_grad
+            E = self.cls_score if e_grad else self._class_matrix()
+            if torch.is_grad_enabled() and (cls_emb.requires_grad or e_grad):
+                # differentiable in both operands like the reference's einsum (:67): with exemplars the
+                # class matrix depends on the learnable lambda_exemplar (st_generalized_rcnn.py:173)
                 cls_logit = embed_logits(cls_emb, E)
             else:
                 out = embed_match_softmax(cls_emb, E, self.score_thresh, want_probs=True, want_logits=True)

@@ -73,7 +73,9 @@ def test_box_candidates_capacity_overflow_is_reported():
     want_off, *_ = oracle.box_candidates(probs, reg, boxes, offs, im, (10., 10., 5., 5.), 0.05, True)
     seg_off, cb, cs, cr, status = _run_candidates(probs, reg, boxes, offs, im, 0.05, True, 16)
     assert status.tolist() == [int(want_off[-1]), 1]          # total reported, nothing written past capacity
-    assert np.array_equal(seg_off.cpu().numpy(), want_off)
+    # on overflow the offsets are clamped to the capacity, so the NMS / selection kernels that follow in
+    # PostProcessor.forward stay inside the cap-sized buffers until the host raises on status[1]
+    assert np.array_equal(seg_off.cpu().numpy(), np.minimum(want_off, 16))
 
 
 @pytest.mark.parametrize("max_det", [100, 7, 0])

@@ -162,3 +162,60 @@ def test_predictor_folded_projection():
         pred.fold_projection(False)
         back, _ = pred(x)
         assert float((back.double() - (want_logits + shift)).abs().max()) < 2e-2 * float((want_logits + shift).abs().max())
+
+
+def _predictor(k, d, thresh=0.05):
+    from types import SimpleNamespace as NS
+    from cvpr22_cross_modal_pseudo_labeling_b200.modeling import FastRCNNPredictor
+    cfg = NS(MODEL=NS(ROI_BOX_HEAD=NS(EMBEDDING_BASED=True, EMB_DIM=d, FREEZE_EMB_PRED=False),
+                      CLS_AGNOSTIC_BBOX_REG=True, ROI_HEADS=NS(SCORE_THRESH=thresh)))
+    return FastRCNNPredictor(cfg, k).cuda()
+
+
+def test_class_matrix_that_requires_grad_gets_its_gradient():
+    """The reference's einsum (roi_box_predictors.py:67) differentiates into the class matrix too; with
+    exemplars it is `combine_embs(...)`, a function of the learnable lambda_exemplar
+    (st_generalized_rcnn.py:173, :372-375).  The drop-in must not drop that gradient."""
+    g = torch.Generator().manual_seed(5)
+    r, k, d, c = 200, 64, 768, 49
+    pred = _predictor(k, d).train()
+    with torch.no_grad():
+        pred.emb_pred.weight.copy_(torch.randn((d, k), generator=g) * 0.1)
+    base = torch.nn.functional.normalize(torch.randn((c, d), generator=g), dim=-1).cuda()
+    exemplar = torch.nn.functional.normalize(torch.randn((c, d), generator=g), dim=-1).cuda()
+    lam = torch.zeros((), device="cuda", requires_grad=True)          # lambda_exemplar starts at 0
+    pred.set_class_embeddings(base + lam * exemplar)                   # combine_embs
+    x = torch.randn((r, k), generator=g).cuda()
+    logits, _ = pred(x)
+    w = torch.randn(logits.shape, generator=g).cuda()
+    (logits * w).sum().backward()
+    emb = pred.emb_pred(x).detach()
+    want = float(((emb @ exemplar.t()) * w).sum())                     # d/d lam of sum(w * emb.(base+lam*ex)^T)
+    assert lam.grad is not None and abs(float(lam.grad) - want) <= 2e-2 * abs(want) + 1e-3
+    assert pred.emb_pred.weight.grad is not None and float(pred.emb_pred.weight.grad.abs().max()) > 0
+    # forward values: bf16 tensor-core product of the same operands
+    ref = emb.to(torch.bfloat16).float() @ base.to(torch.bfloat16).float().t()
+    assert float((logits.detach() - ref).abs().max()) < 2e-2
+
+
+def test_class_matrix_cache_follows_direct_assignment_and_inplace_edits():
+    """The reference assigns `predictor.cls_score = ...` directly (st_generalized_rcnn.py:194): same shape,
+    new values.  The bf16 cache must follow that and in-place edits."""
+    g = torch.Generator().manual_seed(6)
+    r, k, d, c = 64, 32, 768, 18
+    pred = _predictor(k, d).eval()
+    with torch.no_grad():
+        pred.emb_pred.weight.copy_(torch.randn((d, k), generator=g) * 0.1)
+        E1 = torch.nn.functional.normalize(torch.randn((c, d), generator=g), dim=-1).cuda()
+        E2 = torch.nn.functional.normalize(torch.randn((c, d), generator=g), dim=-1).cuda()
+        x = torch.randn((r, k), generator=g).cuda()
+        pred.set_class_embeddings(E1)
+        l1, _ = pred(x)
+        pred.cls_score = E2.clone()               # direct assignment, equal shape
+        l2, _ = pred(x)
+        emb = pred.emb_pred(x).to(torch.bfloat16).float()
+        assert float((l1 - emb @ E1.to(torch.bfloat16).float().t()).abs().max()) < 2e-2
+        assert float((l2 - emb @ E2.to(torch.bfloat16).float().t()).abs().max()) < 2e-2
+        pred.cls_score.mul_(2.0)                  # in-place edit
+        l3, _ = pred(x)
+        assert float((l3 - 2 * (emb @ E2.to(torch.bfloat16).float().t())).abs().max()) < 4e-2

@@ -38,6 +38,17 @@ def test_nms_matches_oracle(n, thr):
     assert np.all(np.diff(got) > 0)  # ascending original indices (nms_cpu.cpp:64)
 
 
+def test_nms_longer_than_one_segment_call(nms_path):
+    """layers.nms is installed over _C.nms for every caller, and the reference takes any N: segments beyond
+    B200_NMS_MAX_SEG run block-recursively (layers/nms.py:_nms_long), keep list still bit-exact, with ties."""
+    if nms_path == "bitmask":
+        pytest.skip("one device path is enough for the 40k-box case")
+    rng = np.random.default_rng(4242)
+    boxes, scores = synth.make_nms_boxes(rng, 40000)
+    for s in (scores, (np.round(scores * 64) / 64).astype(np.float32)):
+        assert np.array_equal(_gpu_nms(boxes, s, 0.5), oracle.nms(boxes, s, 0.5))
+
+
 def test_nms_sorted_input_and_ties():
     rng = np.random.default_rng(7)
     boxes, scores = synth.make_nms_boxes(rng, 3000)
