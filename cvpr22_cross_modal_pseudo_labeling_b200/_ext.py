@@ -41,6 +41,8 @@ SIGNATURES = {
     "b200_roi_align_forward": (_i, [ctypes.POINTER(b200_level), _i, _i, _i, _i, _vp, _i64, _i, _i, _i, _vp, _vp, _vp]),
     "b200_roi_align_forward_fast": (_i, [ctypes.POINTER(b200_level), _i, _i, _i, _i, _vp, _i64, _i, _i, _i, _vp, _vp, _vp]),
     "b200_roi_align_forward_ex": (_i, [ctypes.POINTER(b200_level), _i, _i, _i, _i, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "b200_roi_align_workspace_bytes": (ctypes.c_size_t, [_i64]),
+    "b200_roi_align_forward_ws": (_i, [ctypes.POINTER(b200_level), _i, _i, _i, _i, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, ctypes.c_size_t, _vp]),
     "b200_roi_align_backward": (_i, [ctypes.POINTER(b200_level), _i, _i, _i, _i, _vp, _i64, _i, _i, _i, _vp, _vp]),
     "b200_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "b200_nhwc_to_nchw": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
@@ -52,6 +54,7 @@ SIGNATURES = {
     "b200_select_detections": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "b200_select_topk": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _i, _vp, _vp, _vp, _vp]),
     "b200_embed_match": (_i, [_vp, _vp, _i64, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200_linear_bf16": (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
     "b200_embed_match_wide": (_i, [_vp, _vp, _i64, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
     "b200_paste_masks": (_i, [_vp, _vp, _i64, _i, _i, _i, _i, _f, _vp, _vp]),
     "b200_colmax_decode": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
@@ -82,6 +85,9 @@ def lib():
         if hasattr(l, "b200_debug_rpn"):
             l.b200_debug_rpn.restype = None
             l.b200_debug_rpn.argtypes = [_i]
+        if hasattr(l, "b200_debug_match"):
+            l.b200_debug_match.restype = None
+            l.b200_debug_match.argtypes = [_i]
         if hasattr(l, "b200_debug_nms"):
             l.b200_debug_nms.restype = None
             l.b200_debug_nms.argtypes = [_i]
@@ -123,10 +129,16 @@ def debug_set(force_generic=False, exact=True, variant=0):
       bits 0-3  occupancy variants of the marching kernels (1, 2; 8 = one channel chunk per CTA)
       bit 4     (16) fast math at the FPN box pooler shape: the separable marching kernel instead of
                 the row-streaming kernel
-      bit 5     (32) row-streaming kernel with two channels per consumer thread (28 consumer warps)
+      bit 5     (32) row-streaming kernel visits the RoIs in the order given (no ordering pass)
       bit 6     (64) row-streaming kernel without arithmetic (copy-pipeline probe; output is zeros)
     Process-wide; tests and probes reset it to (False, True, 0)."""
     lib().b200_debug_set(int(force_generic), int(exact), int(variant))
+
+
+def debug_match(legacy=False):
+    """Test hook: SOFTMAX scoring through the one-CTA-per-tile kernel (embed_match.cu) instead of the
+    persistent kernel with overlapped epilogue (tc_gemm.cu)."""
+    lib().b200_debug_match(int(legacy))
 
 
 def debug_nms(force_bitmask=False):

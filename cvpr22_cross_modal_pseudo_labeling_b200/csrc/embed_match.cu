@@ -21,6 +21,7 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "tc_gemm.cuh"
 
 namespace b200 {
 namespace {
@@ -403,8 +404,13 @@ int embed_match_launch(const void* A_bf16, const void* E_bf16, int64_t n_rows, i
                        const int32_t* row_seg, const int32_t* col_seg, const int32_t* row_seg_start,
                        uint64_t* col_best, void* stream);
 
+bool g_match_legacy = false;
+
 }  // namespace
 }  // namespace b200
+
+// Test hook (not part of the reference-facing ABI): SOFTMAX through the one-CTA-per-tile kernel.
+extern "C" void b200_debug_match(int legacy) { b200::g_match_legacy = legacy != 0; }
 
 extern "C" int b200_embed_match(const void* A_bf16, const void* E_bf16, int64_t n_rows, int n_cols, int dim,
                                 int mode, float score_thresh, float* probs, float* logits, int32_t* top_label,
@@ -459,6 +465,11 @@ int embed_match_launch(const void* A_bf16, const void* E_bf16, int64_t n_rows, i
   if (mode == B200_MATCH_COLMAX)
     B200_REQUIRE(row_seg && col_seg && row_seg_start && col_best, "embed_match: COLMAX needs row_seg/col_seg/"
                                                                   "row_seg_start/col_best");
+  // SOFTMAX: the persistent kernel with overlapped epilogue (tc_gemm.cu); g_match_legacy (test hook) keeps
+  // the one-CTA-per-tile kernel below reachable, which also serves COLMAX
+  if (mode == B200_MATCH_SOFTMAX && !g_match_legacy && softmax_gemm_applies(n_cols))
+    return softmax_gemm_launch(A_bf16, E_bf16, n_rows, n_cols, dim, ld, score_thresh, probs, logits, top_label, top_prob,
+                               static_cast<cudaStream_t>(stream));
   MatchParams p;
   p.M = n_rows;
   p.N = n_cols;

@@ -316,7 +316,7 @@ int launch_march(const LevelTable& lt, int C, const float* rois, int64_t n_rois,
 
 template <bool kExact>
 int launch_forward(const LevelTable& lt, int layout, int C, const float* rois, int64_t n_rois, int PH, int PW,
-                   int sr, float* out, float* out_mean, int32_t* out_levels, cudaStream_t st) {
+                   int sr, float* out, float* out_mean, int32_t* out_levels, int32_t* order_ws, cudaStream_t st) {
   const int NB = PH * PW;
   const bool march_ok = !g_force_generic && layout == B200_LAYOUT_NHWC && sr == 2 && PH <= 16 && PW <= 16 &&
                         C % kChunk == 0 && (NB * kChunk) % 4 == 0;
@@ -327,7 +327,7 @@ int launch_forward(const LevelTable& lt, int layout, int C, const float* rois, i
       // -- or when the tuning hook sets g_variant & 16 -- the separable marching kernel
       // (roi_align_fwd_sep.cu)
       if (!(g_variant & 16) && rows_kernel_applies(lt, C, PH, PW))
-        return launch_forward_rows(lt, C, rois, n_rois, out, out_mean, out_levels, g_variant, st);
+        return launch_forward_rows(lt, C, rois, n_rois, out, out_mean, out_levels, order_ws, g_variant, st);
       return launch_forward_sep(lt, C, rois, n_rois, PH, PW, out, out_mean, out_levels, g_variant & 15, st);
     } else {
       // g_variant (tuning hook): CTAs/SM = 6 (default) / 5 / 4 for 128 threads, 3 / 3 / 2 for 256.
@@ -401,7 +401,8 @@ namespace b200 {
 namespace {
 int roi_align_forward_impl(bool exact, const b200_level* levels, int n_levels, int layout, int batch, int channels,
                            const float* rois, int64_t n_rois, int pooled_h, int pooled_w, int sampling_ratio,
-                           float* out, float* out_mean, int32_t* out_levels, void* stream) {
+                           float* out, float* out_mean, int32_t* out_levels, void* workspace, size_t workspace_bytes,
+                           void* stream) {
   B200_REQUIRE(layout == B200_LAYOUT_NCHW || layout == B200_LAYOUT_NHWC, "roi_align: bad layout %d", layout);
   B200_REQUIRE(batch > 0 && channels > 0 && pooled_h > 0 && pooled_w > 0 && n_rois >= 0 && sampling_ratio >= 0,
                "roi_align: bad shape");
@@ -412,10 +413,15 @@ int roi_align_forward_impl(bool exact, const b200_level* levels, int n_levels, i
   int rc = fill_level_table(levels, n_levels, &lt);
   if (rc != B200_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // optional scratch: the RoI visiting order of the row-streaming kernel (ignored when too small)
+  int32_t* order_ws = workspace && workspace_bytes >= rows_order_workspace_bytes(n_rois) &&
+                              (reinterpret_cast<uintptr_t>(workspace) & 3u) == 0
+                          ? static_cast<int32_t*>(workspace)
+                          : nullptr;
   return exact ? launch_forward<true>(lt, layout, channels, rois, n_rois, pooled_h, pooled_w, sampling_ratio, out,
-                                      out_mean, out_levels, st)
+                                      out_mean, out_levels, order_ws, st)
                : launch_forward<false>(lt, layout, channels, rois, n_rois, pooled_h, pooled_w, sampling_ratio,
-                                       out, out_mean, out_levels, st);
+                                       out, out_mean, out_levels, order_ws, st);
 }
 }  // namespace
 }  // namespace b200
@@ -426,7 +432,7 @@ extern "C" int b200_roi_align_forward(const b200_level* levels, int n_levels, in
                                       void* stream) {
   // g_exact is the tuning hook of b200_debug_set; it is true unless a perf script flipped it
   return b200::roi_align_forward_impl(b200::g_exact, levels, n_levels, layout, batch, channels, rois, n_rois,
-                                      pooled_h, pooled_w, sampling_ratio, out, nullptr, out_levels, stream);
+                                      pooled_h, pooled_w, sampling_ratio, out, nullptr, out_levels, nullptr, 0, stream);
 }
 
 extern "C" int b200_roi_align_forward_fast(const b200_level* levels, int n_levels, int layout, int batch,
@@ -434,7 +440,7 @@ extern "C" int b200_roi_align_forward_fast(const b200_level* levels, int n_level
                                            int pooled_w, int sampling_ratio, float* out, int32_t* out_levels,
                                            void* stream) {
   return b200::roi_align_forward_impl(false, levels, n_levels, layout, batch, channels, rois, n_rois, pooled_h,
-                                      pooled_w, sampling_ratio, out, nullptr, out_levels, stream);
+                                      pooled_w, sampling_ratio, out, nullptr, out_levels, nullptr, 0, stream);
 }
 
 extern "C" int b200_roi_align_forward_ex(const b200_level* levels, int n_levels, int layout, int batch, int channels,
@@ -443,5 +449,18 @@ extern "C" int b200_roi_align_forward_ex(const b200_level* levels, int n_levels,
                                          int32_t* out_levels, void* stream) {
   B200_REQUIRE(math == B200_ROI_MATH_EXACT || math == B200_ROI_MATH_FAST, "roi_align: bad math mode %d", math);
   return b200::roi_align_forward_impl(math == B200_ROI_MATH_EXACT, levels, n_levels, layout, batch, channels, rois,
-                                      n_rois, pooled_h, pooled_w, sampling_ratio, out, out_mean, out_levels, stream);
+                                      n_rois, pooled_h, pooled_w, sampling_ratio, out, out_mean, out_levels, nullptr, 0,
+                                      stream);
+}
+
+extern "C" size_t b200_roi_align_workspace_bytes(int64_t n_rois) { return b200::rows_order_workspace_bytes(n_rois); }
+
+extern "C" int b200_roi_align_forward_ws(const b200_level* levels, int n_levels, int layout, int batch, int channels,
+                                         const float* rois, int64_t n_rois, int pooled_h, int pooled_w,
+                                         int sampling_ratio, int math, float* out, float* out_mean,
+                                         int32_t* out_levels, void* workspace, size_t workspace_bytes, void* stream) {
+  B200_REQUIRE(math == B200_ROI_MATH_EXACT || math == B200_ROI_MATH_FAST, "roi_align: bad math mode %d", math);
+  return b200::roi_align_forward_impl(math == B200_ROI_MATH_EXACT, levels, n_levels, layout, batch, channels, rois,
+                                      n_rois, pooled_h, pooled_w, sampling_ratio, out, out_mean, out_levels, workspace,
+                                      workspace_bytes, stream);
 }

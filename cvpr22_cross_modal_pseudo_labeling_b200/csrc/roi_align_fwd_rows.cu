@@ -49,11 +49,10 @@ constexpr int kRC = 256;                         // channels
 constexpr int kPxBytes = kRC * 4;                // one pixel, all channels
 constexpr int kRingPx = 168;                     // byte ring of tap rows, in pixels (1 KB units)
 constexpr int kRingBytes = kRingPx * kPxBytes;
-constexpr int kNBar = 16;                        // ring entries in flight, at most (barrier pairs)
+constexpr int kNBar = 32;                        // ring entries in flight, at most (barrier pairs)
 constexpr int kHist = 64;                        // placement history the planner keeps (> kNBar + kMaxList)
 constexpr int kTabs = 4;                         // RoI tables in flight
-// consumers: thread = (kV channels, output column pw); kV = 4: 14 warps, kV = 2: 28 warps
-constexpr int cons_warps(int v) { return kP * (kRC / v / 32); }
+constexpr int kConsWarps = kP * (kRC / 4 / 32);  // consumers: thread = (4 channels, output column pw): 14 warps
 constexpr int kPlanWarps = 2;  // planner warps, alternating RoIs (one warp's ~900 instructions per RoI bounded the kernel)
 constexpr int kTileFloats = kRC * kBins;
 
@@ -61,20 +60,23 @@ constexpr int kTileFloats = kRC * kBins;
 // Entries are grouped by b (ascending), so the consumers' accumulator indices are compile-time
 // constants; a tap row feeding more than two output rows (bins narrower than ~1.3 pixels) is simply
 // listed -- and copied -- once per pair.
-// `place`: where the planner put the entry in the byte ring; `dep`: the copy may be issued once every
-// ring entry with a sequence number < dep has been given back (entries are given back in order)
+// `place`: where the planner put the entry in the byte ring; `bar`: shared address of the entry's "full"
+// barrier, bit 31 = the phase parity to wait for (the planner knows the entry's sequence number, so the
+// consumers do no barrier arithmetic); RoiTab::dep: the copy may be issued once every ring entry with a
+// sequence number < dep has been given back (entries are given back in order)
 struct __align__(16) RingEntry {
   float w0, w1;
-  uint32_t place, dep;
+  uint32_t place, bar;
 };
 struct __align__(16) RoiTab {
   int nent, ncols, nruns, level;
-  int batch, width, pad0, pad1;
+  int batch, width, roi, pad1;  // roi: the RoI's index (= its output slot)
   int cx[kP][4];    // byte offset inside a slot of the k-th merged tap column of bin pw
   float wx[kP][4];  // its weight (0 for unused entries)
   int nk[8];        // merged tap columns per bin
   int gend[8];      // entries [gend[b-1], gend[b]) feed output rows b, b + 1
-  RingEntry ent[kMaxList];
+  RingEntry ent[kMaxList + 1];  // (+1: the consumers fetch headers one entry ahead)
+  uint32_t dep[kMaxList];
   int ent_y[kMaxList];    // feature row of entry e
   int run_pos[kMaxList], run_col[kMaxList], run_len[kMaxList];  // runs of consecutive tapped columns
 };
@@ -90,6 +92,12 @@ __device__ __forceinline__ V4 lds_v4(uint32_t a) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.lo.x), "=f"(v.lo.y), "=f"(v.hi.x), "=f"(v.hi.y) : "r"(a));
   return v;
 }
+__device__ __forceinline__ uint4 lds_u4(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 __device__ __forceinline__ float2 lds_f2(uint32_t a) {
   float2 v;
   asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
@@ -170,6 +178,11 @@ __device__ __forceinline__ RoiPlace build_rows_tab(const LevelTable& lt, const f
   pl.H = pl.W = 1;
   if (h.level < 0) {  // matches no level: the output rows stay zero (poolers.py:111-119)
     if (lane < 8) tb->gend[lane] = 0;
+    if (lane < 8) tb->nk[lane] = 0;
+    if (lane < kP * 4) {  // (the consumers still fetch the sentinel entry's columns: valid addresses)
+      (&tb->cx[0][0])[lane] = 0;
+      (&tb->wx[0][0])[lane] = 0.f;
+    }
     if (lane == 0) {
       tb->batch = 0;
       tb->width = 1;
@@ -341,8 +354,15 @@ __device__ __forceinline__ RoiPlace build_rows_tab(const LevelTable& lt, const f
 // entries all span ncols pixels and are laid one after the other, wrapping to the start of the ring
 // when the next one would not fit; an entry's copy depends on the newest earlier entry whose bytes it
 // overwrites (found in the placement history) and on the entry that last used its barrier pair.
-__device__ __forceinline__ void place_rows(RoiTab* tb, int lane, RingState* rs) {
+__device__ __forceinline__ void place_rows(RoiTab* tb, int lane, RingState* rs, uint32_t full_a, uint32_t idle_a) {
   const int nent = tb->nent;
+  // sentinel after the last entry: weights 0, a valid ring address, and the parity of a barrier that is
+  // never armed (waiting for the phase "before" the first one passes at once)
+  if (lane == 0) {
+    tb->ent[nent].w0 = tb->ent[nent].w1 = 0.f;
+    tb->ent[nent].place = 0u;
+    tb->ent[nent].bar = idle_a | 0x80000000u;
+  }
   if (nent == 0) return;
   const uint32_t s = (uint32_t)tb->ncols;  // >= 1
   const uint32_t g0 = rs->g0, head = rs->head;
@@ -375,7 +395,8 @@ __device__ __forceinline__ void place_rows(RoiTab* tb, int lane, RingState* rs) 
       }
     }
     tb->ent[lane].place = place * (uint32_t)kPxBytes;
-    tb->ent[lane].dep = dep;
+    tb->ent[lane].bar = (full_a + 8u * (g % (uint32_t)kNBar)) | (((g / (uint32_t)kNBar) & 1u) << 31);
+    tb->dep[lane] = dep;
   }
   if (lane == nent - 1) {
     rs->head = place + s;
@@ -383,29 +404,106 @@ __device__ __forceinline__ void place_rows(RoiTab* tb, int lane, RingState* rs) 
   }
 }
 
+// One RoI's worth of consumer work for a warp whose bin has NK (2..4) merged tap columns.  The entry
+// headers {w0, w1, place, bar} are fetched one entry ahead, the tap columns of the next entry are
+// loaded right after the current one has been reduced along x and given back, and only the two
+// output rows an entry group can touch are kept as accumulators: row b is complete when group b ends
+// and goes to the shared tile at once (`flush`), so the loop over b is a real loop (no unrolling,
+// small code, ~70 registers).
+template <int NK, int kProbe, typename Flush>
+__device__ __forceinline__ void consume_roi(uint32_t ent_a, uint32_t gend_a, uint32_t c0, uint32_t c1, uint32_t c2,
+                                            uint32_t c3, float4 wxv, uint32_t empty_off, int lane, Flush&& flush) {
+  float2 acc0[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, acc1[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+  float2 v[4][2];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v[k][0] = v[k][1] = make_float2(0.f, 0.f);
+  auto load_cols = [&](uint32_t bar, uint32_t off) {
+    mbar_wait_a(bar & 0x7fffffffu, bar >> 31);
+    if (kProbe == 0) {
+      V4 t = lds_v4(c0 + off);
+      v[0][0] = t.lo, v[0][1] = t.hi;
+      t = lds_v4(c1 + off);
+      v[1][0] = t.lo, v[1][1] = t.hi;
+      if (NK > 2) {
+        t = lds_v4(c2 + off);
+        v[2][0] = t.lo, v[2][1] = t.hi;
+      }
+      if (NK > 3) {
+        t = lds_v4(c3 + off);
+        v[3][0] = t.lo, v[3][1] = t.hi;
+      }
+    }
+  };
+  // (the entry after the last one is a sentinel whose barrier always passes: no "is there a next entry"
+  // branch around the loads, so ptxas keeps the tap columns in place instead of copying them)
+  uint4 hdr = lds_u4(ent_a);
+  load_cols(hdr.w, hdr.z);
+  uint32_t ea = ent_a;
+#pragma unroll 1
+  for (int b = 0; b < kP; ++b) {
+    const uint32_t end_a = ent_a + 16u * (uint32_t)lds_i32(gend_a + 4u * b);
+#pragma unroll 1
+    for (; ea < end_a; ea += 16u) {
+      const uint4 nh = lds_u4(ea + 16u);
+      float2 u0 = make_float2(0.f, 0.f), u1 = make_float2(0.f, 0.f);
+      if (kProbe == 0) {
+        const float2 wx0 = make_float2(wxv.x, wxv.x), wx1 = make_float2(wxv.y, wxv.y);
+        u0 = __fmul2_rn(wx0, v[0][0]);
+        u1 = __fmul2_rn(wx0, v[0][1]);
+        u0 = __ffma2_rn(wx1, v[1][0], u0);
+        u1 = __ffma2_rn(wx1, v[1][1], u1);
+        if (NK > 2) {
+          const float2 wx2 = make_float2(wxv.z, wxv.z);
+          u0 = __ffma2_rn(wx2, v[2][0], u0);
+          u1 = __ffma2_rn(wx2, v[2][1], u1);
+        }
+        if (NK > 3) {
+          const float2 wx3 = make_float2(wxv.w, wxv.w);
+          u0 = __ffma2_rn(wx3, v[3][0], u0);
+          u1 = __ffma2_rn(wx3, v[3][1], u1);
+        }
+      }
+      // this entry has been read: give it back, then fetch the next row while this one is accumulated
+      __syncwarp();
+      if (lane == 0) mbar_arrive_a((hdr.w & 0x7fffffffu) + empty_off);
+      load_cols(nh.w, nh.z);
+      const float w0 = __uint_as_float(hdr.x), w1 = __uint_as_float(hdr.y);
+      const float2 w0v = make_float2(w0, w0), w1v = make_float2(w1, w1);
+      acc0[0] = __ffma2_rn(w0v, u0, acc0[0]);
+      acc0[1] = __ffma2_rn(w0v, u1, acc0[1]);
+      acc1[0] = __ffma2_rn(w1v, u0, acc1[0]);
+      acc1[1] = __ffma2_rn(w1v, u1, acc1[1]);
+      hdr = nh;
+    }
+    flush(b, acc0[0], acc0[1]);
+    acc0[0] = acc1[0];
+    acc0[1] = acc1[1];
+    acc1[0] = acc1[1] = make_float2(0.f, 0.f);
+  }
+}
+
 // kCopyWarps: warps issuing the bulk copies (ring entry g belongs to warp g % kCopyWarps -- a single
 // warp's dependent instruction stream, ~40 instructions per entry, was what bounded the first version);
 // kProbe != 0: consumers skip the arithmetic (copy-engine throughput probe)
-template <int kCopyWarps, int kV, int kProbe>
-__global__ void __launch_bounds__(32 * cons_warps(kV) + 32 * kPlanWarps + 32 * kCopyWarps, 1)
-roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, long long n_rois, float* __restrict__ out,
-                   float* __restrict__ out_mean, int32_t* __restrict__ out_levels) {
+template <int kCopyWarps, int kProbe>
+__global__ void __launch_bounds__(32 * kConsWarps + 32 * kPlanWarps + 32 * kCopyWarps, 1)
+roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, const int32_t* __restrict__ order,
+                   long long n_rois, float* __restrict__ out, float* __restrict__ out_mean,
+                   int32_t* __restrict__ out_levels) {
   // (no integer round trip on this pointer: the compiler must keep seeing shared-space addresses,
   // or every access below turns into a generic LD.E / ST.E)
   extern __shared__ __align__(128) unsigned char smem_dyn[];
   __shared__ __align__(128) uint64_t full_bar[kNBar], empty_bar[kNBar], tab_full[kTabs], tab_empty[kTabs];
   __shared__ PlanScratch plan_scratch[kPlanWarps];
   __shared__ RingState ring_state;
-  __shared__ __align__(8) uint64_t place_turn[kPlanWarps];
+  __shared__ __align__(8) uint64_t place_turn[kPlanWarps], idle_bar;
   unsigned char* ring = smem_dyn;
   float* tile = reinterpret_cast<float*>(smem_dyn + (size_t)kRingBytes);
   RoiTab* tabs = reinterpret_cast<RoiTab*>(tile + kTileFloats);
 
-  constexpr int kWarpsPerBin = kRC / kV / 32;
-  constexpr int kConsWarps = cons_warps(kV), kConsThreads = 32 * kConsWarps;
+  constexpr int kConsThreads = 32 * kConsWarps;
   constexpr int kPlanWarp0 = kConsWarps;               // first of the warps that build the RoI tables
   constexpr int kCopyWarp0 = kConsWarps + kPlanWarps;  // first of the warps that issue the bulk copies
-  constexpr int kNP = kV / 2;                 // channel pairs per thread
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s < kNBar; ++s) {
@@ -413,6 +511,7 @@ roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, long lon
       mbar_init(&empty_bar[s], kConsWarps);
     }
     for (int s = 0; s < kPlanWarps; ++s) mbar_init(&place_turn[s], 1);
+    mbar_init(&idle_bar, 1);
     ring_state.g0 = 0;
     ring_state.head = 0;
     for (int s = 0; s < kTabs; ++s) {
@@ -425,20 +524,28 @@ roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, long lon
 
   if (warp >= kPlanWarp0 && warp < kCopyWarp0) {
     // ------------------------------- planners: RoI tables --------------------------------
-    // planner p builds the tables of RoIs n = p, p + kPlanWarps, ...; only the ring placement is
-    // sequential across RoIs: it is done holding the placement turn, passed round-robin
+    // planner p builds the tables of the CTA's RoIs n = p, p + kPlanWarps, ...; only the ring placement
+    // is sequential across RoIs: it is done holding the placement turn, passed round-robin.
+    // `order` (optional): the RoIs are visited in that order (b200_roi_order: image, level, Morton
+    // code of the centre), so the 148 RoIs in flight at any time are neighbours in one feature map
+    // and share its rows through the L2; outputs still go to the RoI's own slot.
     const int p = warp - kPlanWarp0;
+    const uint32_t full_a = smem_u32(full_bar), idle_a = smem_u32(&idle_bar);
     int n = p, k = 0;
-    for (long long r = blockIdx.x + (long long)p * gridDim.x; r < n_rois;
-         r += (long long)kPlanWarps * gridDim.x, n += kPlanWarps, ++k) {
+    for (long long i = blockIdx.x + (long long)p * gridDim.x; i < n_rois;
+         i += (long long)kPlanWarps * gridDim.x, n += kPlanWarps, ++k) {
+      const long long r = order ? (long long)order[i] : i;
       const int ti = n % kTabs;
       mbar_wait(&tab_empty[ti], (uint32_t)(((n / kTabs) & 1) ^ 1));  // (a fresh barrier passes)
       const RoiPlace pl = build_rows_tab(lt, rois, r, tabs + ti, lane, &plan_scratch[p]);
-      if (lane == 0 && out_levels) out_levels[r] = pl.level;
+      if (lane == 0) {
+        tabs[ti].roi = (int)r;
+        if (out_levels) out_levels[r] = pl.level;
+      }
       __syncwarp();
       // my turn: after planner p - 1 placed RoI n - 1 (planner 0's first turn is free)
       mbar_wait(&place_turn[p], (uint32_t)((k & 1) ^ (p == 0 ? 1 : 0)));
-      place_rows(tabs + ti, lane, &ring_state);
+      place_rows(tabs + ti, lane, &ring_state, full_a, idle_a);
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&place_turn[(p + 1) % kPlanWarps]);
@@ -453,7 +560,7 @@ roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, long lon
     const int cw = warp - kCopyWarp0;
     uint32_t g0 = 0;  // ring entries of the RoIs before this one
     int n = 0;
-    for (long long r = blockIdx.x; r < n_rois; r += gridDim.x, ++n) {
+    for (long long i = blockIdx.x; i < n_rois; i += gridDim.x, ++n) {
       const int ti = n % kTabs;
       const RoiTab* tb = tabs + ti;
       mbar_wait(&tab_full[ti], (uint32_t)((n / kTabs) & 1));
@@ -470,15 +577,15 @@ roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, long lon
         }
         const uint32_t size = (uint32_t)ncols * kPxBytes;
         // first entry of this RoI that belongs to this warp
-        int i = (int)((cw + kCopyWarps - g0 % kCopyWarps) % kCopyWarps);
-        for (; i < nent; i += kCopyWarps) {
-          const uint32_t g = g0 + (uint32_t)i, bi = g % kNBar;
-          const uint32_t place = tb->ent[i].place, dep = tb->ent[i].dep;
+        int e = (int)((cw + kCopyWarps - g0 % kCopyWarps) % kCopyWarps);
+        for (; e < nent; e += kCopyWarps) {
+          const uint32_t g = g0 + (uint32_t)e, bi = g % kNBar;
+          const uint32_t place = tb->ent[e].place, dep = tb->dep[e];
           // (dep - 1 >= g - kNBar, so the parity below names one phase unambiguously)
           if (dep > 0) mbar_wait(&empty_bar[(dep - 1u) % kNBar], ((dep - 1u) / kNBar) & 1u);
           if (lane == 0) mbar_arrive_expect_tx(&full_bar[bi], size);
           if (lane < nruns)
-            bulk_g2s(ring + place + my_pos, gbase + (size_t)tb->ent_y[i] * width * kPxBytes, my_len, &full_bar[bi]);
+            bulk_g2s(ring + place + my_pos, gbase + (size_t)tb->ent_y[e] * width * kPxBytes, my_len, &full_bar[bi]);
         }
         g0 += (uint32_t)nent;
       }
@@ -489,173 +596,164 @@ roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, long lon
   }
 
   // --------------------------------- consumers --------------------------------------------
-  const int pw = warp / kWarpsPerBin;
-  const int q = (warp % kWarpsPerBin) * 32 + lane;
-  const int rot = kV == 4 ? (lane >> 3) & 3 : (lane >> 4) & 1;
+  // thread = (channel quad q, output column pw): two warps per pw, a warp's lanes read 512 contiguous
+  // bytes of a pixel (conflict-free LDS.128)
+  const int pw = warp >> 1;
+  const int q = (warp & 1) * 32 + lane;
+  const int rot = (lane >> 3) & 3;
   // 32-bit shared addresses, pinned in registers (ptxas otherwise re-derives them from the CTA's
   // shared window at every use)
-  uint32_t ring_a = smem_u32(ring) + q * (4 * kV), full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
-  uint32_t tabs_a = smem_u32(tabs);
-  asm volatile("" : "+r"(ring_a), "+r"(full_a), "+r"(empty_a), "+r"(tabs_a));
+  uint32_t ring_a = smem_u32(ring) + q * 16, tabs_a = smem_u32(tabs);
+  uint32_t empty_off = smem_u32(empty_bar) - smem_u32(full_bar);
+  // tile slots of the thread's four channels, rotated by lane / 8 so that the 32 lanes of a store hit
+  // 32 different banks (thread stride 4 * 49 floats = 4 mod 32, channel stride 49 = 17 mod 32)
+  uint32_t tc0, tc1, tc2, tc3;
+  {
+    const uint32_t t0 = smem_u32(tile) + 4u * (uint32_t)((4 * q) * kBins + pw);
+    tc0 = t0 + 4u * (uint32_t)(((0 + rot) & 3) * kBins);
+    tc1 = t0 + 4u * (uint32_t)(((1 + rot) & 3) * kBins);
+    tc2 = t0 + 4u * (uint32_t)(((2 + rot) & 3) * kBins);
+    tc3 = t0 + 4u * (uint32_t)(((3 + rot) & 3) * kBins);
+  }
+  asm volatile("" : "+r"(ring_a), "+r"(tabs_a), "+r"(tc0), "+r"(tc1), "+r"(tc2), "+r"(tc3), "+r"(empty_off));
   const uint64_t store_policy = policy_evict_first();
-  uint32_t g = 0;   // ring entry to load into registers next
-  uint32_t rg = 0;  // ring entry to give back next
+  // output row b of this thread's (4 channels, pw) is complete: into the tile.  Before the first row
+  // of a RoI the bulk store of the previous RoI must have read the tile.
+  auto flush = [&](int b, float2 lo, float2 hi) {
+    if (b == 0) {
+      if (tid == 0) bulk_wait_read();
+      bar_consumers<kConsThreads>();
+    }
+    float a = lo.x, bb = lo.y, c = hi.x, d = hi.y;
+    if (rot & 1) {
+      const float t = a;
+      a = bb;
+      bb = c;
+      c = d;
+      d = t;
+    }
+    if (rot & 2) {
+      float t = a;
+      a = c;
+      c = t;
+      t = bb;
+      bb = d;
+      d = t;
+    }
+    const uint32_t o = 4u * (uint32_t)(b * kP);
+    sts_f32(tc0 + o, a);
+    sts_f32(tc1 + o, bb);
+    sts_f32(tc2 + o, c);
+    sts_f32(tc3 + o, d);
+  };
   int n = 0;
-  for (long long r = blockIdx.x; r < n_rois; r += gridDim.x, ++n) {
+  for (long long i = blockIdx.x; i < n_rois; i += gridDim.x, ++n) {
     const int ti = n % kTabs;
     const RoiTab* tb = tabs + ti;
     const uint32_t tb_a = tabs_a + (uint32_t)ti * (uint32_t)sizeof(RoiTab);
     mbar_wait(&tab_full[ti], (uint32_t)((n / kTabs) & 1));
-    const int nent = tb->nent;
+    const long long r = tb->roi;
     const int4 cxv = *reinterpret_cast<const int4*>(tb->cx[pw]);
     const float4 wxv = *reinterpret_cast<const float4*>(tb->wx[pw]);
     const int nk = tb->nk[pw];
     const uint32_t c0 = ring_a + cxv.x, c1 = ring_a + cxv.y, c2 = ring_a + cxv.z, c3 = ring_a + cxv.w;
-    const float2 wx0 = make_float2(wxv.x, wxv.x), wx1 = make_float2(wxv.y, wxv.y), wx2 = make_float2(wxv.z, wxv.z),
-                 wx3 = make_float2(wxv.w, wxv.w);
-    float2 acc2[kP][kNP];  // [output row][channel pair]
-#pragma unroll
-    for (int ph = 0; ph < kP; ++ph)
-#pragma unroll
-      for (int c = 0; c < kNP; ++c) acc2[ph][c] = make_float2(0.f, 0.f);
-    float2 v[4][kNP];  // [tap column][channel pair]
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-#pragma unroll
-      for (int c = 0; c < kNP; ++c) v[k][c] = make_float2(0.f, 0.f);
-    auto lds_col = [&](int k, uint32_t a) {
-      if (kV == 4) {
-        const V4 t = lds_v4(a);
-        v[k][0] = t.lo;
-        v[k][kNP - 1] = t.hi;
-      } else {
-        v[k][0] = lds_v2(a);
-      }
-    };
-    // the tap columns of bin pw of the next ring entry -> registers
-    auto load_row = [&](uint32_t off) {
-      const uint32_t bi = g % kNBar;
-      mbar_wait_a(full_a + 8u * bi, (g / kNBar) & 1u);
-      if (kProbe == 0) {
-        // (loading all four columns unconditionally -- unused ones repeat the first with weight 0 --
-        // was measured 15 % slower: shared-memory wavefronts matter more than the two branches)
-        lds_col(0, c0 + off);
-        lds_col(1, c1 + off);
-        if (nk > 2) lds_col(2, c2 + off);
-        if (nk > 3) lds_col(3, c3 + off);
-      }
-      ++g;
-    };
-    uint32_t ent_a = tb_a + (uint32_t)offsetof(RoiTab, ent);
-    const uint32_t ent_last = ent_a + 16u * (uint32_t)(nent - 1);
-    if (nent > 0) load_row((uint32_t)lds_i32(ent_a + 8u));
-#pragma unroll
-    for (int b = 0; b < kP; ++b) {
-      const uint32_t end_a = tb_a + (uint32_t)offsetof(RoiTab, ent) + 16u * (uint32_t)lds_i32(tb_a + (uint32_t)offsetof(RoiTab, gend) + 4u * b);
-      for (; ent_a < end_a; ent_a += 16) {
-        const float2 w = lds_f2(ent_a);
-        const uint32_t next_off = (uint32_t)lds_i32(ent_a + 16u + 8u);  // (past the last entry: unused)
-        // x pass: the tap columns reduced to one value per channel
-        float2 u[kNP];
-#pragma unroll
-        for (int c = 0; c < kNP; ++c) u[c] = make_float2(0.f, 0.f);
-        if (kProbe == 0) {
-#pragma unroll
-          for (int c = 0; c < kNP; ++c) {
-            u[c] = __fmul2_rn(wx0, v[0][c]);
-            u[c] = __ffma2_rn(wx1, v[1][c], u[c]);
-          }
-          if (nk > 2) {
-#pragma unroll
-            for (int c = 0; c < kNP; ++c) u[c] = __ffma2_rn(wx2, v[2][c], u[c]);
-          }
-          if (nk > 3) {
-#pragma unroll
-            for (int c = 0; c < kNP; ++c) u[c] = __ffma2_rn(wx3, v[3][c], u[c]);
-          }
-        }
-        // this entry has been read: give it back, then fetch the next row while this one is accumulated
-        __syncwarp();
-        if (lane == 0) mbar_arrive_a(empty_a + 8u * (rg % kNBar));
-        ++rg;
-        if (ent_a < ent_last) load_row(next_off);
-        // y pass
-        const float2 w0 = make_float2(w.x, w.x);
-#pragma unroll
-        for (int c = 0; c < kNP; ++c) acc2[b][c] = __ffma2_rn(w0, u[c], acc2[b][c]);
-        if (b + 1 < kP) {
-          const float2 w1 = make_float2(w.y, w.y);
-#pragma unroll
-          for (int c = 0; c < kNP; ++c) acc2[b + 1][c] = __ffma2_rn(w1, u[c], acc2[b + 1][c]);
-        }
-      }
-    }
+    const uint32_t ent_a = tb_a + (uint32_t)offsetof(RoiTab, ent), gend_a = tb_a + (uint32_t)offsetof(RoiTab, gend);
+    // (nk is the same for the whole warp: one specialised loop per RoI, no per-entry branches)
+    if (nk > 3) consume_roi<4, kProbe>(ent_a, gend_a, c0, c1, c2, c3, wxv, empty_off, lane, flush);
+    else if (nk > 2) consume_roi<3, kProbe>(ent_a, gend_a, c0, c1, c2, c3, wxv, empty_off, lane, flush);
+    else consume_roi<2, kProbe>(ent_a, gend_a, c0, c1, c2, c3, wxv, empty_off, lane, flush);
     // the tables of this RoI are no longer needed
     __syncwarp();
     if (lane == 0) mbar_arrive(&tab_empty[ti]);
 
-    // ---- epilogue: registers -> [256 x 49] tile -> one contiguous block of the output -------
-    if (tid == 0) bulk_wait_read();  // the bulk store of the previous RoI has read the tile
-    bar_consumers<kConsThreads>();
-    {
-      // lane groups write different channels of their thread's kV in one instruction (rotation by
-      // lane / 8 for kV = 4, lane / 16 for kV = 2): the 32 lanes then hit 32 different banks
-      // (thread stride 49 * kV floats = kV mod 32, channel stride 49 = 17 mod 32)
-      float* t0 = tile + (kV * q) * kBins + pw;
-      float* tc[kV];
-#pragma unroll
-      for (int j = 0; j < kV; ++j) tc[j] = t0 + ((j + rot) % kV) * kBins;
-#pragma unroll
-      for (int ph = 0; ph < kP; ++ph) {
-        if (kV == 4) {
-          float a = acc2[ph][0].x, b = acc2[ph][0].y, c = acc2[ph][kNP - 1].x, d = acc2[ph][kNP - 1].y;
-          if (rot & 1) {
-            const float t = a;
-            a = b;
-            b = c;
-            c = d;
-            d = t;
-          }
-          if (rot & 2) {
-            float t = a;
-            a = c;
-            c = t;
-            t = b;
-            b = d;
-            d = t;
-          }
-          tc[0][ph * kP] = a;
-          tc[1][ph * kP] = b;
-          tc[kV - 2][ph * kP] = c;
-          tc[kV - 1][ph * kP] = d;
-        } else {
-          float a = acc2[ph][0].x, b = acc2[ph][0].y;
-          if (rot & 1) {
-            const float t = a;
-            a = b;
-            b = t;
-          }
-          tc[0][ph * kP] = a;
-          tc[1][ph * kP] = b;
-        }
-      }
-    }
-    // one contiguous 50 KB block of the NCHW output: a single bulk store (TMA) drains the tile while
-    // the consumers are already in the next RoI's rows
+    // ---- the [256 x 49] tile is complete: one contiguous 50 KB block of the NCHW output, a single
+    // bulk store (TMA) that drains while the consumers are already in the next RoI's rows ----
     fence_proxy_async();  // this thread's tile writes -> visible to the async proxy
     bar_consumers<kConsThreads>();
-    {
-      if (tid == 0) bulk_s2g(out + (size_t)r * kTileFloats, smem_u32(tile), kTileFloats * 4, store_policy);
-      if (out_mean && tid < kRC) {
-        const float* row = tile + tid * kBins;
-        float s = 0.f;
+    if (tid == 0) bulk_s2g(out + (size_t)r * kTileFloats, smem_u32(tile), kTileFloats * 4, store_policy);
+    if (out_mean && tid < kRC) {
+      const float* row = tile + tid * kBins;
+      float s = 0.f;
 #pragma unroll 7
-        for (int i = 0; i < kBins; ++i) s = __fadd_rn(s, row[i]);
-        out_mean[(size_t)r * kRC + tid] = __fdiv_rn(s, (float)kBins);
-      }
+      for (int j = 0; j < kBins; ++j) s = __fadd_rn(s, row[j]);
+      out_mean[(size_t)r * kRC + tid] = __fdiv_rn(s, (float)kBins);
     }
   }
   if (tid == 0) bulk_wait_all();  // the last store must have left shared memory before the CTA exits
+}
+
+// ---------------------------------------------------------------------------------------------
+// Visiting order of the RoIs for the row-streaming kernel: chunks of kOrderChunk consecutive RoIs are
+// bucketed by (image, FPN level, cell of a 16 x 16 grid over the level's map in Morton order) with a
+// counting sort in shared memory -- histogram with shared atomics, one scan, one scatter (~3 us; a
+// bitonic sort of the same chunk took 42 us).  The order inside a bucket is whatever the atomics give:
+// it only decides which SM takes which RoI when, never a result.
+// ---------------------------------------------------------------------------------------------
+constexpr int kOrderChunk = 2048, kOrderThreads = 1024, kOrderBuckets = 4096;
+
+__global__ void __launch_bounds__(kOrderThreads) roi_order_kernel(const LevelTable lt, const float* __restrict__ rois,
+                                                                  long long n_rois, int32_t* __restrict__ order) {
+  __shared__ int hist[kOrderBuckets];
+  __shared__ int warp_tot[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long base = (long long)blockIdx.x * kOrderChunk;
+  const int n = (int)min((long long)kOrderChunk, n_rois - base);
+  for (int i = tid; i < kOrderBuckets; i += kOrderThreads) hist[i] = 0;
+  __syncthreads();
+  const int img0 = (int)rois[base * 5];  // buckets are relative to the chunk's first image
+  int bucket[kOrderChunk / kOrderThreads], slot[kOrderChunk / kOrderThreads];
+#pragma unroll
+  for (int k = 0; k < kOrderChunk / kOrderThreads; ++k) {
+    const int i = tid + k * kOrderThreads;
+    bucket[k] = -1;
+    if (i < n) {
+      const RoiHeader h = load_roi(rois, base + i, lt);
+      const int l = h.level < 0 ? 0 : h.level;
+      const float sx = lt.scale[l] * 16.f / (float)lt.W[l], sy = lt.scale[l] * 16.f / (float)lt.H[l];
+      const int cx = (int)fminf(fmaxf((h.x1 + h.x2) * 0.5f * sx, 0.f), 15.f), cy = (int)fminf(fmaxf((h.y1 + h.y2) * 0.5f * sy, 0.f), 15.f);
+      int m = 0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) m |= (((cx >> b) & 1) << (2 * b)) | (((cy >> b) & 1) << (2 * b + 1));
+      bucket[k] = ((((h.batch - img0) & 3) << 2 | ((h.level + 1) & 3)) << 8) | m;
+      slot[k] = atomicAdd(&hist[bucket[k]], 1);
+    }
+  }
+  __syncthreads();
+  // exclusive scan of the 4096 counters: 4 per thread, warp scan, scan of the warp totals
+  int c[4], run = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    c[j] = hist[4 * tid + j];
+    run += c[j];
+  }
+  int incl = run;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = warp_tot[lane];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, w, d);
+      if (lane >= d) w += t;
+    }
+    warp_tot[lane] = w;
+  }
+  __syncthreads();
+  int ex = incl - run + (warp > 0 ? warp_tot[warp - 1] : 0);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    hist[4 * tid + j] = ex;
+    ex += c[j];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kOrderChunk / kOrderThreads; ++k)
+    if (bucket[k] >= 0) order[base + hist[bucket[k]] + slot[k]] = (int32_t)(base + tid + k * kOrderThreads);
 }
 
 }  // namespace
@@ -667,25 +765,34 @@ bool rows_kernel_applies(const LevelTable& lt, int C, int PH, int PW) {
 
 // Preconditions (checked by the caller): NHWC, sampling_ratio 2; rows_kernel_applies().
 int launch_forward_rows(const LevelTable& lt, int C, const float* rois, int64_t n_rois, float* out, float* out_mean,
-                        int32_t* out_levels, int variant, cudaStream_t st) {
+                        int32_t* out_levels, int32_t* order_ws, int variant, cudaStream_t st) {
   B200_REQUIRE(C == kRC, "roi_align rows kernel: %d channels", C);
-  const int64_t grid = n_rois < sm_count() ? n_rois : sm_count();
-#define B200_ROWS(CW, V, PROBE)                                                                                   \
-  do {                                                                                                            \
-    static SmemHighWater hw;                                                                                      \
-    int rc = ensure_dynamic_smem(roi_align_fwd_rows<CW, V, PROBE>, kRowsSmem, &hw, "roi_align rows: smem");       \
-    if (rc != B200_OK) return rc;                                                                                 \
-    roi_align_fwd_rows<CW, V, PROBE><<<(unsigned)grid, 32 * cons_warps(V) + 32 * kPlanWarps + 32 * CW, kRowsSmem, st>>>(       \
-        lt, rois, (long long)n_rois, out, out_mean, out_levels);                                                  \
-  } while (0)
-  // variant (tuning hook of b200_debug_set): bit 5 = two channels per consumer thread (28 consumer warps),
+  B200_REQUIRE(n_rois < ((int64_t)1 << 31), "roi_align rows kernel: too many RoIs");
+  // variant (tuning hook of b200_debug_set): bit 5 = visit the RoIs in the order given (no b200 ordering pass),
   // bit 6 = copy-engine probe (no arithmetic)
-  if (variant & 64) B200_ROWS(2, 4, 1);
-  else if (variant & 32) B200_ROWS(2, 2, 0);
-  else B200_ROWS(2, 4, 0);
+  const int32_t* order = nullptr;
+  if (order_ws && !(variant & 32) && n_rois > 1) {
+    roi_order_kernel<<<(unsigned)ceil_div<int64_t>(n_rois, kOrderChunk), kOrderThreads, 0, st>>>(lt, rois, (long long)n_rois,
+                                                                                              order_ws);
+    B200_CHECK_LAUNCH("roi_order_kernel");
+    order = order_ws;
+  }
+  const int64_t grid = n_rois < sm_count() ? n_rois : sm_count();
+#define B200_ROWS(CW, PROBE)                                                                                    \
+  do {                                                                                                          \
+    static SmemHighWater hw;                                                                                    \
+    int rc = ensure_dynamic_smem(roi_align_fwd_rows<CW, PROBE>, kRowsSmem, &hw, "roi_align rows: smem");        \
+    if (rc != B200_OK) return rc;                                                                               \
+    roi_align_fwd_rows<CW, PROBE><<<(unsigned)grid, 32 * kConsWarps + 32 * kPlanWarps + 32 * CW, kRowsSmem, st>>>( \
+        lt, rois, order, (long long)n_rois, out, out_mean, out_levels);                                         \
+  } while (0)
+  if (variant & 64) B200_ROWS(2, 1);
+  else B200_ROWS(2, 0);
 #undef B200_ROWS
   B200_CHECK_LAUNCH("roi_align_fwd_rows");
   return B200_OK;
 }
+
+size_t rows_order_workspace_bytes(int64_t n_rois) { return n_rois > 0 ? sizeof(int32_t) * (size_t)n_rois : 0; }
 
 }  // namespace b200

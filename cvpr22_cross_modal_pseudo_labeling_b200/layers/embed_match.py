@@ -17,6 +17,9 @@ def _bf16(t, name):
     _ext.require_cuda(t, name)
     if t.dim() != 2:
         raise ValueError("%s must be 2-D" % name)
+    pre = getattr(t, "b200_bf16", None)   # TensorCoreLinear hands its bf16 output along with the fp32 one
+    if pre is not None and pre.shape == t.shape and pre.device == t.device:
+        return pre
     return t.to(torch.bfloat16).contiguous()
 
 

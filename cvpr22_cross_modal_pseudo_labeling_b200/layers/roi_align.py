@@ -71,6 +71,19 @@ def _check_inputs(feats, rois):
             raise ValueError("all levels must share batch and channel sizes")
 
 
+_ws_cache = {}
+
+
+def _workspace(nbytes, device):
+    """Grow-only scratch buffer per (device, stream); the torch caching allocator owns the memory."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
 def _forward(feats, scales, rois, output_size, sampling_ratio, want_levels=False, math=None, mean_out=None):
     """-> (pooled [R,C,PH,PW], levels or None).  mean_out: optional preallocated [R,C] fp32 tensor that
     receives the per-channel mean over the bins (b200_roi_align_forward_ex, fused AvgPool2d)."""
@@ -92,19 +105,17 @@ def _forward(feats, scales, rois, output_size, sampling_ratio, want_levels=False
     levels_out = torch.empty((r,), dtype=torch.int32, device=dev) if want_levels else None
     if r > 0:
         arr = _levels_array(tensors, scales)
+        if mean_out is not None and (mean_out.shape != (r, c) or mean_out.dtype != torch.float32 or
+                                     not mean_out.is_contiguous() or mean_out.device != dev):
+            raise ValueError("mean_out must be a contiguous float32 [R,C] tensor on the input's device")
+        lib = _ext.lib()
+        # scratch for the RoI visiting order of the row-streaming kernel (grow-only, per device and stream)
+        ws = _workspace(lib.b200_roi_align_workspace_bytes(r), dev) if math == "fast" else None
         with torch.cuda.device(dev):
-            if mean_out is not None:
-                if (mean_out.shape != (r, c) or mean_out.dtype != torch.float32 or not mean_out.is_contiguous()
-                        or mean_out.device != dev):
-                    raise ValueError("mean_out must be a contiguous float32 [R,C] tensor on the input's device")
-                rc = _ext.lib().b200_roi_align_forward_ex(
-                    arr, len(tensors), layout, feats[0].size(0), c, _ext.ptr(rois), r, ph, pw, int(sampling_ratio),
-                    MATH_MODES.index(math), _ext.ptr(out), _ext.ptr(mean_out), _ext.ptr(levels_out),
-                    _ext.stream_ptr(dev))
-            else:
-                fn = _ext.lib().b200_roi_align_forward if math == "exact" else _ext.lib().b200_roi_align_forward_fast
-                rc = fn(arr, len(tensors), layout, feats[0].size(0), c, _ext.ptr(rois), r, ph, pw,
-                        int(sampling_ratio), _ext.ptr(out), _ext.ptr(levels_out), _ext.stream_ptr(dev))
+            rc = lib.b200_roi_align_forward_ws(
+                arr, len(tensors), layout, feats[0].size(0), c, _ext.ptr(rois), r, ph, pw, int(sampling_ratio),
+                MATH_MODES.index(math), _ext.ptr(out), _ext.ptr(mean_out), _ext.ptr(levels_out), _ext.ptr(ws),
+                ws.numel() if ws is not None else 0, _ext.stream_ptr(dev))
         _ext.check(rc, "b200_roi_align_forward")
     return out, levels_out
 

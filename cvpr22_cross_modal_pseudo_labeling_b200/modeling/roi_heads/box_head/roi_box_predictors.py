@@ -16,7 +16,7 @@ parts against ones in the activations).  Same tolerance bars as the unfolded pat
 import torch
 from torch import nn
 
-from ....layers import embed_logits, embed_match_softmax
+from ....layers import TensorCoreLinear, embed_logits, embed_match_softmax
 
 
 def _get(cfg, path, default=None):
@@ -37,7 +37,8 @@ class FastRCNNPredictor(nn.Module):
         cls_agnostic = bool(_get(config, "MODEL.CLS_AGNOSTIC_BBOX_REG", True))
         if self.embedding_based:
             self.emb_dim = int(_get(config, "MODEL.ROI_BOX_HEAD.EMB_DIM", 768))
-            self.emb_pred = nn.Linear(in_channels, self.emb_dim)
+            # nn.Linear (same parameters) whose product runs on tcgen05 in front of the scoring kernel
+            self.emb_pred = TensorCoreLinear(in_channels, self.emb_dim)
             nn.init.normal_(self.emb_pred.weight, mean=0, std=0.01)
             nn.init.constant_(self.emb_pred.bias, 0)
             assert cls_agnostic

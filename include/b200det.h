@@ -120,6 +120,23 @@ int b200_roi_align_forward_ex(const b200_level* levels, int n_levels, int layout
                               float* out_mean, int32_t* out_levels, void* stream);
 
 /*
+ * b200_roi_align_forward_ex with caller-provided scratch (b200_roi_align_workspace_bytes(n_rois) bytes,
+ * 4-byte aligned; NULL / too small = b200_roi_align_forward_ex).  The row-streaming kernel (fast math,
+ * 256 NHWC channels, 7x7, sampling ratio 2) uses it for the order in which it visits the RoIs: sorted by
+ * (image, FPN level, Morton code of the box centre), so the RoIs in flight on the 148 SMs at any time
+ * are neighbours in one feature map and share its rows through the L2 (DRAM traffic ~ the touched
+ * features once).  Results are written to every RoI's own slot: the output does not depend on it.
+ * The reference allocates inside the op (csrc/cuda/ROIAlign_cuda.cu:271); here the caller owns all memory.
+ */
+size_t b200_roi_align_workspace_bytes(int64_t n_rois);
+int b200_roi_align_forward_ws(const b200_level* levels, int n_levels, int layout,
+                              int batch, int channels, const float* rois,
+                              int64_t n_rois, int pooled_h, int pooled_w,
+                              int sampling_ratio, int math, float* out,
+                              float* out_mean, int32_t* out_levels, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
+/*
  * Fused multi-level RoIAlign backward (gradient w.r.t. the features).
  * Replaces _C.roi_align_backward (csrc/ROIAlign.h:27-45; kernel
  * csrc/cuda/ROIAlign_cuda.cu:178-254, host :302-346) for every level at once.
@@ -232,6 +249,20 @@ int b200_embed_match(const void* A_bf16, const void* E_bf16, int64_t n_rows,
                      float* top_prob, const int32_t* row_seg,
                      const int32_t* col_seg, const int32_t* row_seg_start,
                      uint64_t* col_best, void* stream);
+/*
+ * y = x . W^T + b on the tcgen05 tensor cores (bf16 operands, fp32 accumulation in TMEM, persistent
+ * warp-specialised kernel with double-buffered accumulators, csrc/tc_gemm.cu): the `emb_pred` projection
+ * nn.Linear(in, EMB_DIM) of FastRCNNPredictor that runs in front of the scoring product
+ * (modeling/roi_heads/box_head/roi_box_predictors.py:63-66; called on its own by
+ * detector/st_generalized_rcnn.py:226-228), and -- with transposed operands -- its two gradient GEMMs.
+ *   A [n_rows, dim] bf16 row-major, W [n_out, dim] bf16 row-major (nn.Linear's weight layout), both
+ *   16-byte aligned, dim % 8 == 0; bias [n_out] fp32 or NULL;
+ *   out_bf16 [n_rows, n_out] bf16 and / or out_f32 [n_rows, n_out] fp32 (at least one).
+ */
+int b200_linear_bf16(const void* A_bf16, const void* W_bf16, const float* bias,
+                     int64_t n_rows, int n_out, int dim, void* out_bf16,
+                     float* out_f32, void* stream);
+
 /*
  * SOFTMAX scoring against a class matrix of ANY width (e.g. the 1203-word LVIS vocabulary the
  * student scores caption images against, detector/st_generalized_rcnn.py:71-75,:191): logits are

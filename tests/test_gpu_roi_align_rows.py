@@ -46,7 +46,7 @@ EDGE = np.array([
 ], dtype=np.float32)
 
 
-# 0: four channels per consumer thread (14 consumer warps); 32: two channels (28 consumer warps)
+# 0: RoIs visited in the library's own order (image, level, Morton code of the centre); 32: in the order given
 LAYOUTS = [0, 32]
 
 
@@ -99,6 +99,24 @@ def test_rows_kernel_small_grids_and_mean(n, layout):
     assert torch.allclose(mean, pooled.mean(dim=(2, 3)), rtol=1e-5, atol=1e-6)
     again, _ = _fwd(feats, synth.FPN_SCALES, rois, ROWS | layout)
     assert torch.equal(again, pooled)
+
+
+@pytest.mark.timeout(120)
+def test_rows_kernel_visiting_order_does_not_change_results():
+    """The ordering pass only decides which SM takes which RoI when; every RoI is computed from its own
+    tables and written to its own slot, so results are bit-identical with and without it, for RoIs given
+    in any order (shuffled across images, more than one sort chunk of 4096)."""
+    rng = np.random.default_rng(2607)
+    feats = _pyramid(rng, 3, 256)
+    rois = synth.make_rois(rng, 1700, 3)
+    rois = torch.from_numpy(rois[rng.permutation(len(rois))]).cuda()
+    a, la = _fwd(feats, synth.FPN_SCALES, rois, ROWS, want_levels=True)
+    b, lb = _fwd(feats, synth.FPN_SCALES, rois, ROWS | 32, want_levels=True)
+    assert torch.equal(a, b) and torch.equal(la, lb)
+    want, wl = oracle.pooler_forward([f.cpu().contiguous().numpy() for f in feats], rois[:300].cpu().numpy(),
+                                     synth.FPN_SCALES, 7, 7, 2)
+    np.testing.assert_allclose(a[:300].cpu().numpy(), want, rtol=RTOL, atol=1e-6)
+    assert np.array_equal(la[:300].cpu().numpy(), wl)
 
 
 @pytest.mark.timeout(180)
