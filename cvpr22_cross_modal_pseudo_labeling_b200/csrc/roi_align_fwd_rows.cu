@@ -786,6 +786,8 @@ int launch_forward_rows(const LevelTable& lt, int C, const float* rois, int64_t 
     roi_align_fwd_rows<CW, PROBE><<<(unsigned)grid, 32 * kConsWarps + 32 * kPlanWarps + 32 * CW, kRowsSmem, st>>>( \
         lt, rois, order, (long long)n_rois, out, out_mean, out_levels);                                         \
   } while (0)
+  // (L2 prefetch of the planned rows -- bulk prefetches from the planner or one RoI ahead from a copy warp,
+  // and LSU-side prefetch.global.L2 -- was measured 10-45 % SLOWER in all three forms: DESIGN.md)
   if (variant & 64) B200_ROWS(2, 1);
   else B200_ROWS(2, 0);
 #undef B200_ROWS

@@ -27,7 +27,7 @@
 //     probabilities = e * exp(block max - row max) / sum, streamed from the stash with full-row
 //     coalescing (a warp per row) and from TMEM for the last block.
 // Numerics: fp32 accumulation of bf16 products (as embed_match_kernel); exp2f of (l - max) * log2(e);
-// the stash rounds e in (0, 1] to fp16 (relative 2^-11: far inside the 2e-2 absolute bar of BASELINE.json).
+// e in (0, 1] is cut to fp16 precision (relative 2^-10: far inside the 2e-2 absolute bar of BASELINE.json).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -290,29 +290,39 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
         } else {
           const bool last = blk == p.nblk - 1;
-          // ---- sweep A: row max and best foreground column (>= 1; first maximum wins) over my columns ----
-          float mx = -INFINITY, best = -INFINITY;
-          int bestc = 0;
+          // ---- sweep A: row max and best foreground column (>= 1; first maximum wins) over my columns:
+          // compare, max, select of the in-chunk index per element; the chunk is noted once per chunk
+          // (tcgen05.ld is warp-collective with one address: a per-lane reload of "my best chunk" is impossible)
+          float best = -INFINITY, bg = -INFINITY;
+          int besti = 0, bestchunk = 0;
           for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
             tmem_ld16(taddr + c0, v);
+            const int c = col0 + c0;
+            if (c + 16 > p.N) {  // the row's last chunk: padded columns do not count
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (c + i >= p.N) v[i] = -INFINITY;
+            }
+            if (c == 0) {  // column 0 is the background row: in the row max, not among the labels
+              bg = v[0];
+              v[0] = -INFINITY;
+            }
+            const float before = best;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const int c = col0 + c0 + i;
-              if (c < p.N) {
-                mx = fmaxf(mx, v[i]);
-                if (c >= 1 && v[i] > best) {
-                  best = v[i];
-                  bestc = c;
-                }
-              }
+              besti = v[i] > best ? i : besti;
+              best = fmaxf(best, v[i]);
             }
+            bestchunk = best > before ? c : bestchunk;
           }
+          const float mx = fmaxf(best, bg);
+          const int bestc = bestchunk + besti;
           stats->mx[blk][ch][trow] = mx;
           stats->best[blk][ch][trow] = best;
           stats->bestc[blk][ch][trow] = bestc;
           bar_named(1 + quad, 64);  // the two column halves of this quadrant
           const float mxb = fmaxf(stats->mx[blk][0][trow], stats->mx[blk][1][trow]);
-          // ---- sweep B: e = exp(l - block max) rounded to fp16, row sum of the ROUNDED values (so the
+          // ---- sweep B: e = exp(l - block max) cut to fp16 precision, row sum of the CUT values (so the
           // probabilities still add up to one to fp32 accuracy); raw logits out; e parked in the stash, or --
           // for the row's last block, whose turn at the stash comes later -- written back to its TMEM columns
           float sum = 0.f;
@@ -335,16 +345,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               }
               __syncwarp();
             }
+            // e truncated to 11 significant bits (one LOP): exactly representable in fp16, so the parked
+            // values, the TMEM copy and the row sum all see the same numbers
+            const bool tail = c + 16 > p.N;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float e = exp2f(fmaf(v[i], kLog2e, -moff));
+              if (tail && c + i >= p.N) e = 0.f;
+              e = __uint_as_float(__float_as_uint(e) & 0xFFFFE000u);
+              sum += e;
+              v[i] = e;
+            }
             uint32_t w[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float e0 = c + 2 * i < p.N ? exp2f(fmaf(v[2 * i], kLog2e, -moff)) : 0.f;
-              const float e1 = c + 2 * i + 1 < p.N ? exp2f(fmaf(v[2 * i + 1], kLog2e, -moff)) : 0.f;
-              const __half2 t = __floats2half2_rn(e0, e1);
-              const float2 back = __half22float2(t);
-              sum += back.x + back.y;
-              v[2 * i] = back.x;
-              v[2 * i + 1] = back.y;
+              const __half2 t = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
               w[i] = *reinterpret_cast<const uint32_t*>(&t);
             }
             if (last && p.nblk > 1) {
@@ -404,6 +419,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               const float f = stats->fac[b][r];
               const __half* src = reinterpret_cast<const __half*>(stash + (size_t)r * kStashPitch);
               float* o = p.probs + orow * p.ld + b * p.BN;
+#pragma unroll 4
               for (int c = lane; c < ncol; c += 32) o[c] = __half2float(src[c]) * f;
             }
           };
