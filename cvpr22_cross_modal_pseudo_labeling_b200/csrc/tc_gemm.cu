@@ -16,9 +16,10 @@
 //   * persistent CTAs (one per SM), each walks row tiles m, m + grid, ...; a row tile is processed as
 //     column blocks of <= 256 columns, so TMEM holds TWO accumulator buffers (2 x 256 columns):
 //     the MMAs of unit j + 1 run while the epilogue warps drain unit j (acc_full / acc_empty mbarriers);
-//   * warp 0 = TMA producer (A box 128 x 64, B box BN x 64, 128-byte swizzle, ring of smem stages),
-//     warp 1 = MMA issuer (one lane, tcgen05.mma.kind::f16, M = 128, N = block width, K = 16 x 4 per stage),
-//     warps 2-9 = epilogue: 2 warps per TMEM lane quadrant, each owns half of the block's columns;
+//   * warps 0, 1 = TMA producers (A box 128 x 64 / B box BN x 64, 128-byte swizzle, ring of smem stages),
+//     warp 2 = MMA issuer (one lane, tcgen05.mma.kind::f16, M = 128, N = block width, K = 16 x 4 per stage),
+//     warps 3-18 = epilogue: 4 warps per TMEM lane quadrant, each owns a quarter of the block's columns
+//     (with 8 epilogue warps -- two per scheduler -- the sweeps of a 128 x 256 block took longer than its MMAs);
 //   * SOFTMAX over up to two column blocks without a second GEMM pass and with ONE exp per element:
 //     per block, sweep A = row max + best foreground column, sweep B = e = exp(l - block max) and the
 //     row sum.  A block that is not the row's last parks e as fp16 in shared memory ("stash") and frees
@@ -41,8 +42,10 @@ namespace {
 constexpr int kBM = 128;    // rows per tile (= TMEM lanes)
 constexpr int kBK = 64;     // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int kUmmaK = 16;  // K of one tcgen05.mma.kind::f16
-constexpr int kEpiWarps = 8;
-constexpr int kGemmThreads = 32 * (2 + kEpiWarps);
+constexpr int kEpiWarps = 16;
+constexpr int kCH = kEpiWarps / 4;  // epilogue warps per TMEM lane quadrant: each owns 1 / kCH of a block's columns
+constexpr int kFirstEpiWarp = 3;  // warps 0, 1: TMA producers (A / B operand), warp 2: MMA issuer
+constexpr int kGemmThreads = 32 * (kFirstEpiWarp + kEpiWarps);
 constexpr int kMaxStages = 8;
 constexpr int kMaxBN = 256;
 constexpr int kStashPitch = 2 * kMaxBN + 16;  // bytes per stash row: 256 fp16 + 16 (rows shift by 4 banks)
@@ -128,14 +131,33 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// mbarrier wait that parks the thread in hardware until the phase completes (suspend-time hint), instead of
+// re-issuing try_wait from a spin loop: with 19 warps per SM the polling of the waiting roles took a fifth
+// of the issue slots away from the epilogue warps (profiles/r02_match_cfg5_probs.txt)
+__device__ __forceinline__ void mbar_wait_park(uint64_t* bar, uint32_t phase) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@!p bra WAIT_%=;\n\t}" ::"r"(smem_u32(bar)),
+      "r"(phase), "r"(0x989680u)
+      : "memory");
+}
+// 2^x for x <= 0: one MUFU.EX2 (exp2f() adds range fix-ups for arguments the softmax never produces)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void bar_named(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
 // per-row statistics of the softmax epilogue, [block][column half][row]
+// (12 KB: with the 66 KB stash this still leaves three 48 KB pipeline stages at 512 columns)
 struct SoftStats {
-  float mx[2][2][kBM];
-  float sum[2][2][kBM];
-  float best[2][2][kBM];
-  int bestc[2][2][kBM];
+  float sum[2][kCH][kBM];
+  float best[2][kCH][kBM];       // best foreground logit of the part (-inf if it has none)
+  uint16_t bestc[2][kCH][kBM];   // its column
+  float bg[2][kBM];              // logit of column 0 (the background row) in block 0, -inf in block 1
   float fac[2][kBM];  // probability = e * fac[block][row]
 };
 
@@ -150,6 +172,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int num_kb = (p.K + kBK - 1) / kBK;
   const long long n_mtiles = (p.M + kBM - 1) / kBM;
   const int NP = (p.N + 15) / 16 * 16;
+  // work units: SOFTMAX keeps all column blocks of a row tile on one CTA (row statistics); LINEAR hands out
+  // (row tile, column block) units one by one -- 500 tiles x 3 blocks over 148 CTAs is 10.1 units each,
+  // whole row tiles would be 3.4 (one CTA in three does a fourth: 84 % at best)
+  const long long n_outer = EPI == kEpiLinear ? n_mtiles * p.nblk : n_mtiles;
+  const int n_inner = EPI == kEpiLinear ? 1 : p.nblk;
   // dynamic shared memory may start at any 16-byte boundary: realign for the 128 B swizzle
   unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~uintptr_t(1023));
   // SOFTMAX only: fp16 stash of e = exp(l - max), row statistics, per-warp transpose tiles for the logits
@@ -159,7 +186,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], 2);  // one arrive.expect_tx per producer warp
       mbar_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -168,7 +195,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     fence_mbar_init();
   }
-  if (warp == 1) {
+  if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
                  "r"((uint32_t)p.tmem_cols)
                  : "memory");
@@ -179,37 +206,44 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
-  if (warp == 0) {
-    // ===== TMA producer =====
+  if (warp < 2) {
+    // ===== TMA producers: warp 0 streams the A tiles, warp 1 the B tiles.  One thread issues a bulk tensor
+    // copy every ~250-500 cycles whatever its size (scripts/micro/tma_box.cu): with both operands on one
+    // thread the 32 requests of a 128 x 512 tile took longer than its MMAs =====
     if (lane == 0) {
       uint32_t it = 0;
-      for (long long mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x)
-        for (int blk = 0; blk < p.nblk; ++blk)
+      const uint32_t my_bytes = warp == 0 ? p.a_bytes : p.stage_bytes - p.a_bytes;
+      const CUtensorMap* map = warp == 0 ? &map_a : &map_b;
+      for (long long o = blockIdx.x; o < n_outer; o += gridDim.x)
+        for (int in = 0; in < n_inner; ++in) {
+          const long long mt = EPI == kEpiLinear ? o / p.nblk : o;
+          const int blk = EPI == kEpiLinear ? (int)(o % p.nblk) : in;
           for (int kb = 0; kb < num_kb; ++kb, ++it) {
             const int s = it % p.stages;
             const uint32_t ph = (it / p.stages) & 1;
-            mbar_wait(&empty_bar[s], ph ^ 1);  // first pass falls through (barrier still in phase 0)
-            unsigned char* a_dst = tiles + (size_t)s * p.stage_bytes;
-            mbar_arrive_expect_tx(&full_bar[s], p.stage_bytes);
-            tma_load_2d(a_dst, &map_a, &full_bar[s], kb * kBK, (int)(mt * kBM));
-            tma_load_2d(a_dst + p.a_bytes, &map_b, &full_bar[s], kb * kBK, blk * p.BN);
+            mbar_wait_park(&empty_bar[s], ph ^ 1);  // first pass falls through (barrier still in phase 0)
+            unsigned char* dst = tiles + (size_t)s * p.stage_bytes + (warp == 0 ? 0u : p.a_bytes);
+            mbar_arrive_expect_tx(&full_bar[s], my_bytes);
+            tma_load_2d(dst, map, &full_bar[s], kb * kBK, warp == 0 ? (int)(mt * kBM) : blk * p.BN);
           }
+        }
     }
-  } else if (warp == 1) {
+  } else if (warp == 2) {
     // ===== MMA issuer (one elected lane) =====
     if (lane == 0) {
       uint32_t it = 0, j = 0;
-      for (long long mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x)
-        for (int blk = 0; blk < p.nblk; ++blk, ++j) {
+      for (long long o = blockIdx.x; o < n_outer; o += gridDim.x)
+        for (int in = 0; in < n_inner; ++in, ++j) {
+          const int blk = EPI == kEpiLinear ? (int)(o % p.nblk) : in;
           const int buf = j & 1;
-          mbar_wait(&acc_empty[buf], ((j >> 1) & 1) ^ 1);  // the epilogue has drained this buffer
+          mbar_wait_park(&acc_empty[buf], ((j >> 1) & 1) ^ 1);  // the epilogue has drained this buffer
           tc_fence_after();
           const int bn = min(p.BN, NP - blk * p.BN);
           const uint32_t idesc = umma_idesc(bn);
           const uint32_t d_addr = tmem_base + (uint32_t)(buf * p.buf_stride);
           for (int kb = 0; kb < num_kb; ++kb, ++it) {
             const int s = it % p.stages;
-            mbar_wait(&full_bar[s], (it / p.stages) & 1);
+            mbar_wait_park(&full_bar[s], (it / p.stages) & 1);
             tc_fence_after();
             const uint32_t a_addr = smem_u32(tiles + (size_t)s * p.stage_bytes);
             const uint32_t b_addr = a_addr + p.a_bytes;
@@ -225,21 +259,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else {
     // ===== epilogue: thread <-> TMEM lane <-> row of the tile; two warps per lane quadrant =====
     const int quad = warp & 3;          // a warp may only touch TMEM lanes [32 * (warp % 4), +32)
-    const int ch = (warp - 2) >> 2;     // which half of the block's columns
+    const int ch = (warp - kFirstEpiWarp) >> 2;  // which part of the block's columns
     const int trow = quad * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
     uint32_t j = 0;
-    for (long long mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
+    for (long long o = blockIdx.x; o < n_outer; o += gridDim.x) {
+      const long long mt = EPI == kEpiLinear ? o / p.nblk : o;
       const long long row = mt * kBM + trow;
       const bool row_ok = row < p.M;
-      for (int blk = 0; blk < p.nblk; ++blk, ++j) {
+      for (int in = 0; in < n_inner; ++in, ++j) {
+        const int blk = EPI == kEpiLinear ? (int)(o % p.nblk) : in;
         const int buf = j & 1;
         const int col0 = blk * p.BN;
         const int bn = min(p.BN, NP - col0);
-        const int half = ((bn / 16 + 1) / 2) * 16;
-        const int c_lo = ch ? half : 0, c_hi = ch ? bn : half;
+        const int part = ((bn / 16 + kCH - 1) / kCH) * 16;
+        const int c_lo = min(ch * part, bn), c_hi = min(c_lo + part, bn);
         const uint32_t taddr = lane_addr + (uint32_t)(buf * p.buf_stride);
-        mbar_wait(&acc_full[buf], (j >> 1) & 1);
+        mbar_wait_park(&acc_full[buf], (j >> 1) & 1);
         tc_fence_after();
         float v[16];
         if (EPI == kEpiLinear) {
@@ -315,13 +351,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             bestchunk = best > before ? c : bestchunk;
           }
-          const float mx = fmaxf(best, bg);
           const int bestc = bestchunk + besti;
-          stats->mx[blk][ch][trow] = mx;
           stats->best[blk][ch][trow] = best;
-          stats->bestc[blk][ch][trow] = bestc;
-          bar_named(1 + quad, 64);  // the two column halves of this quadrant
-          const float mxb = fmaxf(stats->mx[blk][0][trow], stats->mx[blk][1][trow]);
+          stats->bestc[blk][ch][trow] = (uint16_t)bestc;
+          if (ch == 0) stats->bg[blk][trow] = bg;
+          bar_named(1 + quad, 32 * kCH);  // the two column halves of this quadrant
+          float mxb = stats->bg[blk][trow];
+#pragma unroll
+          for (int h = 0; h < kCH; ++h) mxb = fmaxf(mxb, stats->best[blk][h][trow]);
           // ---- sweep B: e = exp(l - block max) cut to fp16 precision, row sum of the CUT values (so the
           // probabilities still add up to one to fp32 accuracy); raw logits out; e parked in the stash, or --
           // for the row's last block, whose turn at the stash comes later -- written back to its TMEM columns
@@ -333,7 +370,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (p.logits) {
               // a thread holds 16 columns of ITS row; transposed through a warp-private tile so that half a
               // warp writes 64 contiguous bytes of one row (2 rows per store instruction)
-              float* tt = xpose + (warp - 2) * (32 * 17);
+              float* tt = xpose + (warp - kFirstEpiWarp) * (32 * 17);
 #pragma unroll
               for (int i = 0; i < 16; ++i) tt[lane * 17 + i] = v[i];
               __syncwarp();
@@ -347,12 +384,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             // e truncated to 11 significant bits (one LOP): exactly representable in fp16, so the parked
             // values, the TMEM copy and the row sum all see the same numbers
-            const bool tail = c + 16 > p.N;
+            if (c + 16 > p.N) {  // the row's last chunk: padded columns contribute nothing
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (c + i >= p.N) v[i] = -INFINITY;
+            }
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              float e = exp2f(fmaf(v[i], kLog2e, -moff));
-              if (tail && c + i >= p.N) e = 0.f;
-              e = __uint_as_float(__float_as_uint(e) & 0xFFFFE000u);
+              const float e = __uint_as_float(__float_as_uint(ex2_approx(fmaf(v[i], kLog2e, -moff))) & 0xFFFFE000u);
               sum += e;
               v[i] = e;
             }
@@ -380,15 +419,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           } else {
             tmem_wait_st();
           }
-          bar_named(1 + quad, 64);  // sums and stash rows of this quadrant are visible
+          bar_named(1 + quad, 32 * kCH);  // sums and stash rows of this quadrant are visible
           // ---- the row's statistics over all blocks ----
-          float rmx = -INFINITY;
-          for (int b = 0; b < p.nblk; ++b) rmx = fmaxf(rmx, fmaxf(stats->mx[b][0][trow], stats->mx[b][1][trow]));
+          float bmax[2] = {-INFINITY, -INFINITY}, bsum[2] = {0.f, 0.f};
+          for (int b = 0; b < p.nblk; ++b) {
+            bmax[b] = stats->bg[b][trow];
+#pragma unroll
+            for (int h = 0; h < kCH; ++h) {
+              bmax[b] = fmaxf(bmax[b], stats->best[b][h][trow]);
+              bsum[b] += stats->sum[b][h][trow];
+            }
+          }
+          const float rmx = fmaxf(bmax[0], bmax[1]);
           float tot = 0.f, fb[2] = {0.f, 0.f};
           for (int b = 0; b < p.nblk; ++b) {
-            const float bm = fmaxf(stats->mx[b][0][trow], stats->mx[b][1][trow]);
-            fb[b] = exp2f((bm - rmx) * kLog2e);
-            tot += fb[b] * (stats->sum[b][0][trow] + stats->sum[b][1][trow]);
+            fb[b] = ex2_approx((bmax[b] - rmx) * kLog2e);
+            tot += fb[b] * bsum[b];
           }
           const float inv = 1.0f / tot;
           if (ch == 0) {
@@ -397,37 +443,49 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               float bb = -INFINITY;
               int bc = 0;
               for (int b = 0; b < p.nblk; ++b)
-                for (int h = 0; h < 2; ++h)
+                for (int h = 0; h < kCH; ++h)
                   if (stats->best[b][h][trow] > bb) {  // blocks / halves in column order: the first maximum wins
                     bb = stats->best[b][h][trow];
                     bc = stats->bestc[b][h][trow];
                   }
-              const float bp = p.N > 1 ? exp2f((bb - rmx) * kLog2e) * inv : 0.f;
+              const float bp = p.N > 1 ? ex2_approx((bb - rmx) * kLog2e) * inv : 0.f;
               p.top_label[row] = (p.N > 1 && bp > p.score_thresh) ? bc : 0;
               if (p.top_prob) p.top_prob[row] = bp;
             }
           }
-          bar_named(1 + quad, 64);  // fac[] written
+          bar_named(1 + quad, 32 * kCH);  // fac[] written
           // ---- probabilities: e * fac, streamed from the stash a warp per row, lanes along the columns
           // (every store instruction writes 128 contiguous bytes of one row, whatever the row pitch) ----
+          // (a lane takes the column pairs (2l, 2l + 1) + 64k: one 32-bit shared load, two conversions, two
+          // multiplies, two stores per pair -- a row pitch like 501 floats leaves no wider aligned store)
+          const uint32_t stash_a = smem_u32(stash);
           auto stream = [&](int b, int ncol) {
             if (!p.probs) return;
-            for (int rr = ch; rr < 32; rr += 2) {
+            for (int rr = ch; rr < 32; rr += kCH) {
               const int r = quad * 32 + rr;
               const long long orow = mt * kBM + r;
               if (orow >= p.M) break;
               const float f = stats->fac[b][r];
-              const __half* src = reinterpret_cast<const __half*>(stash + (size_t)r * kStashPitch);
-              float* o = p.probs + orow * p.ld + b * p.BN;
-#pragma unroll 4
-              for (int c = lane; c < ncol; c += 32) o[c] = __half2float(src[c]) * f;
+              const uint32_t src = stash_a + (uint32_t)r * kStashPitch + 4u * (uint32_t)lane;
+              float* o = p.probs + orow * p.ld + b * p.BN + 2 * lane;
+#pragma unroll
+              for (int k = 0; k < kMaxBN / 64; ++k) {
+                const int c = 2 * lane + 64 * k;
+                if (c < ncol) {
+                  uint32_t w;
+                  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(src + 128u * k));
+                  const float2 e = __half22float2(*reinterpret_cast<const __half2*>(&w));
+                  o[64 * k] = e.x * f;
+                  if (c + 1 < ncol) o[64 * k + 1] = e.y * f;
+                }
+              }
             }
           };
           if (p.nblk == 1) {
             stream(0, p.N);
           } else {
             stream(0, p.BN);
-            bar_named(1 + quad, 64);  // the parked block has left the stash
+            bar_named(1 + quad, 32 * kCH);  // the parked block has left the stash
             // the last block: TMEM -> stash (exact: the values are fp16 already), then the same streaming
             if (p.probs) {
               for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
@@ -446,18 +504,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
-            bar_named(1 + quad, 64);
+            bar_named(1 + quad, 32 * kCH);
             stream(blk, p.N - col0);
           }
           // the statistics and stash rows of this quadrant may be overwritten by the next tile
-          bar_named(1 + quad, 64);
+          bar_named(1 + quad, 32 * kCH);
         }
       }
     }
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
   }
@@ -529,8 +587,8 @@ int launch(GemmParams& p, const void* A, const void* B, size_t extra_smem, cudaS
   static SmemHighWater hw;
   rc = ensure_dynamic_smem(tc_gemm_kernel<EPI>, smem, &hw, "tc_gemm: smem attribute");
   if (rc != B200_OK) return rc;
-  const long long n_mtiles = (p.M + kBM - 1) / kBM;
-  const long long grid = n_mtiles < sm_count() ? n_mtiles : sm_count();
+  const long long n_units = (p.M + kBM - 1) / kBM * (EPI == kEpiLinear ? p.nblk : 1);
+  const long long grid = n_units < sm_count() ? n_units : sm_count();
   tc_gemm_kernel<EPI><<<(unsigned)grid, kGemmThreads, smem, st>>>(map_a, map_b, p);
   B200_CHECK_LAUNCH("tc_gemm_kernel");
   return B200_OK;
