@@ -15,6 +15,7 @@ B200_LAYOUT_NCHW = 0
 B200_LAYOUT_NHWC = 1
 B200_MAX_LEVELS = 8
 B200_NMS_MAX_SEG = 16384
+B200_ERR_UNSUPPORTED = -4
 B200_MATCH_SOFTMAX = 0
 B200_MATCH_COLMAX = 1
 
@@ -43,6 +44,7 @@ SIGNATURES = {
     "b200_roi_align_forward_ex": (_i, [ctypes.POINTER(b200_level), _i, _i, _i, _i, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "b200_roi_align_workspace_bytes": (ctypes.c_size_t, [_i64]),
     "b200_roi_align_forward_ws": (_i, [ctypes.POINTER(b200_level), _i, _i, _i, _i, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, ctypes.c_size_t, _vp]),
+    "b200_roi_align_forward_bf16": (_i, [ctypes.POINTER(b200_level), _i, _i, _i, _i, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, ctypes.c_size_t, _vp]),
     "b200_roi_align_backward": (_i, [ctypes.POINTER(b200_level), _i, _i, _i, _i, _vp, _i64, _i, _i, _i, _vp, _vp]),
     "b200_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "b200_nhwc_to_nchw": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),

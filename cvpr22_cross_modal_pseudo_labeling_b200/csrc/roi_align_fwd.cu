@@ -327,7 +327,7 @@ int launch_forward(const LevelTable& lt, int layout, int C, const float* rois, i
       // -- or when the tuning hook sets g_variant & 16 -- the separable marching kernel
       // (roi_align_fwd_sep.cu)
       if (!(g_variant & 16) && rows_kernel_applies(lt, C, PH, PW))
-        return launch_forward_rows(lt, C, rois, n_rois, out, out_mean, out_levels, order_ws, g_variant, st);
+        return launch_forward_rows(lt, C, false, rois, n_rois, out, out_mean, out_levels, order_ws, g_variant, st);
       return launch_forward_sep(lt, C, rois, n_rois, PH, PW, out, out_mean, out_levels, g_variant & 15, st);
     } else {
       // g_variant (tuning hook): CTAs/SM = 6 (default) / 5 / 4 for 128 threads, 3 / 3 / 2 for 256.
@@ -451,6 +451,30 @@ extern "C" int b200_roi_align_forward_ex(const b200_level* levels, int n_levels,
   return b200::roi_align_forward_impl(math == B200_ROI_MATH_EXACT, levels, n_levels, layout, batch, channels, rois,
                                       n_rois, pooled_h, pooled_w, sampling_ratio, out, out_mean, out_levels, nullptr, 0,
                                       stream);
+}
+
+extern "C" int b200_roi_align_forward_bf16(const b200_level* levels, int n_levels, int layout, int batch, int channels,
+                                           const float* rois, int64_t n_rois, int pooled_h, int pooled_w,
+                                           int sampling_ratio, float* out, float* out_mean, int32_t* out_levels,
+                                           void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace b200;
+  B200_REQUIRE(batch > 0 && channels > 0 && pooled_h > 0 && pooled_w > 0 && n_rois >= 0, "roi_align: bad shape");
+  if (n_rois == 0) return B200_OK;
+  B200_REQUIRE(rois && out && aligned16(out), "roi_align: null rois / out, or out not 16-byte aligned");
+  LevelTable lt;
+  int rc = fill_level_table(levels, n_levels, &lt);
+  if (rc != B200_OK) return rc;
+  if (layout != B200_LAYOUT_NHWC || sampling_ratio != 2 || !rows_kernel_applies(lt, channels, pooled_h, pooled_w)) {
+    set_error("roi_align bf16: only NHWC maps with 256 channels, 7x7 bins and sampling ratio 2 have a bf16 kernel "
+              "(cast other shapes to fp32, as the reference does)");
+    return B200_ERR_UNSUPPORTED;
+  }
+  int32_t* order_ws = workspace && workspace_bytes >= rows_order_workspace_bytes(n_rois) &&
+                              (reinterpret_cast<uintptr_t>(workspace) & 3u) == 0
+                          ? static_cast<int32_t*>(workspace)
+                          : nullptr;
+  return launch_forward_rows(lt, channels, true, rois, n_rois, out, out_mean, out_levels, order_ws, g_variant,
+                             static_cast<cudaStream_t>(stream));
 }
 
 extern "C" size_t b200_roi_align_workspace_bytes(int64_t n_rois) { return b200::rows_order_workspace_bytes(n_rois); }

@@ -89,8 +89,8 @@ int launch_forward_sep(const LevelTable& lt, int C, const float* rois, int64_t n
 
 // roi_align_fwd_rows.cu
 bool rows_kernel_applies(const LevelTable& lt, int C, int PH, int PW);
-int launch_forward_rows(const LevelTable& lt, int C, const float* rois, int64_t n_rois, float* out, float* out_mean,
-                        int32_t* out_levels, int32_t* order_ws, int variant, cudaStream_t st);
+int launch_forward_rows(const LevelTable& lt, int C, bool bf16_maps, const float* rois, int64_t n_rois, float* out,
+                        float* out_mean, int32_t* out_levels, int32_t* order_ws, int variant, cudaStream_t st);
 size_t rows_order_workspace_bytes(int64_t n_rois);
 
 }  // namespace b200

@@ -46,9 +46,10 @@ constexpr int kNS = 2 * kP;                      // samples per axis
 constexpr int kBins = kP * kP;                   // 49
 constexpr int kMaxList = 2 * kNS;                // distinct tap rows / columns of a RoI, at most
 constexpr int kRC = 256;                         // channels
-constexpr int kPxBytes = kRC * 4;                // one pixel, all channels
-constexpr int kRingPx = 168;                     // byte ring of tap rows, in pixels (1 KB units)
-constexpr int kRingBytes = kRingPx * kPxBytes;
+constexpr int kRingBytes = 168 * 1024;           // byte ring of tap rows
+// kPxB (template parameter below): bytes of one pixel, all channels -- 1024 for fp32 maps, 512 for bf16 maps
+// (bf16 in, fp32 arithmetic and output: the reference's amp.float_function semantics on bf16-rounded inputs,
+// layers/roi_align.py:57); the ring then holds twice as many pixels
 constexpr int kNBar = 32;                        // ring entries in flight, at most (barrier pairs)
 constexpr int kHist = 64;                        // placement history the planner keeps (> kNBar + kMaxList)
 constexpr int kTabs = 4;                         // RoI tables in flight
@@ -98,6 +99,17 @@ __device__ __forceinline__ uint4 lds_u4(uint32_t a) {
   return v;
 }
 __device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+// four channels of a pixel: 16 bytes of fp32, or 8 bytes of bf16 widened to fp32 (a shift / a mask per value)
+template <int kPxB>
+__device__ __forceinline__ V4 lds_px(uint32_t a) {
+  if (kPxB == kRC * 4) return lds_v4(a);
+  uint32_t lo, hi;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(a));
+  V4 v;
+  v.lo = make_float2(__uint_as_float(lo << 16), __uint_as_float(lo & 0xffff0000u));
+  v.hi = make_float2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u));
+  return v;
+}
 __device__ __forceinline__ float2 lds_f2(uint32_t a) {
   float2 v;
   asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
@@ -169,6 +181,7 @@ struct __align__(16) RingState {
   uint32_t hist_place[kHist], hist_size[kHist];  // placement of the last kHist entries (pixels)
 };
 
+template <int kPxB>
 __device__ __forceinline__ RoiPlace build_rows_tab(const LevelTable& lt, const float* __restrict__ rois, long long r,
                                                    RoiTab* tb, int lane, PlanScratch* sc) {
   const RoiHeader h = load_roi(rois, r, lt);
@@ -270,7 +283,7 @@ __device__ __forceinline__ RoiPlace build_rows_tab(const LevelTable& lt, const f
 #pragma unroll
           for (int s = 0; s < 4; ++s)
             if (s == m) {
-              cxo[s] = idx[k] * kPxBytes;
+              cxo[s] = idx[k] * kPxB;
               wxo[s] = w[k];
             }
           ++m;
@@ -346,6 +359,7 @@ __device__ __forceinline__ RoiPlace build_rows_tab(const LevelTable& lt, const f
       tb->nruns = __popc(smask);
       tb->level = h.level;
     }
+
   }
   return pl;
 }
@@ -354,7 +368,9 @@ __device__ __forceinline__ RoiPlace build_rows_tab(const LevelTable& lt, const f
 // entries all span ncols pixels and are laid one after the other, wrapping to the start of the ring
 // when the next one would not fit; an entry's copy depends on the newest earlier entry whose bytes it
 // overwrites (found in the placement history) and on the entry that last used its barrier pair.
+template <int kPxB>
 __device__ __forceinline__ void place_rows(RoiTab* tb, int lane, RingState* rs, uint32_t full_a, uint32_t idle_a) {
+  constexpr int kRingPx = kRingBytes / kPxB;
   const int nent = tb->nent;
   // sentinel after the last entry: weights 0, a valid ring address, and the parity of a barrier that is
   // never armed (waiting for the phase "before" the first one passes at once)
@@ -394,7 +410,7 @@ __device__ __forceinline__ void place_rows(RoiTab* tb, int lane, RingState* rs, 
         break;  // older overlapping entries only give smaller values
       }
     }
-    tb->ent[lane].place = place * (uint32_t)kPxBytes;
+    tb->ent[lane].place = place * (uint32_t)kPxB;
     tb->ent[lane].bar = (full_a + 8u * (g % (uint32_t)kNBar)) | (((g / (uint32_t)kNBar) & 1u) << 31);
     tb->dep[lane] = dep;
   }
@@ -410,7 +426,7 @@ __device__ __forceinline__ void place_rows(RoiTab* tb, int lane, RingState* rs, 
 // output rows an entry group can touch are kept as accumulators: row b is complete when group b ends
 // and goes to the shared tile at once (`flush`), so the loop over b is a real loop (no unrolling,
 // small code, ~70 registers).
-template <int NK, int kProbe, typename Flush>
+template <int NK, int kProbe, int kPxB, typename Flush>
 __device__ __forceinline__ void consume_roi(uint32_t ent_a, uint32_t gend_a, uint32_t c0, uint32_t c1, uint32_t c2,
                                             uint32_t c3, float4 wxv, uint32_t empty_off, int lane, Flush&& flush) {
   float2 acc0[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, acc1[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
@@ -420,16 +436,16 @@ __device__ __forceinline__ void consume_roi(uint32_t ent_a, uint32_t gend_a, uin
   auto load_cols = [&](uint32_t bar, uint32_t off) {
     mbar_wait_a(bar & 0x7fffffffu, bar >> 31);
     if (kProbe == 0) {
-      V4 t = lds_v4(c0 + off);
+      V4 t = lds_px<kPxB>(c0 + off);
       v[0][0] = t.lo, v[0][1] = t.hi;
-      t = lds_v4(c1 + off);
+      t = lds_px<kPxB>(c1 + off);
       v[1][0] = t.lo, v[1][1] = t.hi;
       if (NK > 2) {
-        t = lds_v4(c2 + off);
+        t = lds_px<kPxB>(c2 + off);
         v[2][0] = t.lo, v[2][1] = t.hi;
       }
       if (NK > 3) {
-        t = lds_v4(c3 + off);
+        t = lds_px<kPxB>(c3 + off);
         v[3][0] = t.lo, v[3][1] = t.hi;
       }
     }
@@ -466,6 +482,7 @@ __device__ __forceinline__ void consume_roi(uint32_t ent_a, uint32_t gend_a, uin
       // this entry has been read: give it back, then fetch the next row while this one is accumulated
       __syncwarp();
       if (lane == 0) mbar_arrive_a((hdr.w & 0x7fffffffu) + empty_off);
+      // (a first poll of the next entry's barrier before this entry's arithmetic was measured slower)
       load_cols(nh.w, nh.z);
       const float w0 = __uint_as_float(hdr.x), w1 = __uint_as_float(hdr.y);
       const float2 w0v = make_float2(w0, w0), w1v = make_float2(w1, w1);
@@ -475,6 +492,8 @@ __device__ __forceinline__ void consume_roi(uint32_t ent_a, uint32_t gend_a, uin
       acc1[1] = __ffma2_rn(w1v, u1, acc1[1]);
       hdr = nh;
     }
+    // (holding completed rows back for two groups, so that the first flush of a RoI never waits for the bulk
+    // store of the previous one, was measured 2 % slower: registers and moves cost more than the wait)
     flush(b, acc0[0], acc0[1]);
     acc0[0] = acc1[0];
     acc0[1] = acc1[1];
@@ -485,11 +504,12 @@ __device__ __forceinline__ void consume_roi(uint32_t ent_a, uint32_t gend_a, uin
 // kCopyWarps: warps issuing the bulk copies (ring entry g belongs to warp g % kCopyWarps -- a single
 // warp's dependent instruction stream, ~40 instructions per entry, was what bounded the first version);
 // kProbe != 0: consumers skip the arithmetic (copy-engine throughput probe)
-template <int kCopyWarps, int kProbe>
+template <int kCopyWarps, int kProbe, int kPxB>
 __global__ void __launch_bounds__(32 * kConsWarps + 32 * kPlanWarps + 32 * kCopyWarps, 1)
 roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, const int32_t* __restrict__ order,
                    long long n_rois, float* __restrict__ out, float* __restrict__ out_mean,
-                   int32_t* __restrict__ out_levels) {
+                   int32_t* __restrict__ out_levels, int flags) {
+  // flags (probe, b200_debug_set variant bit 8): 1 = the output tile is not stored
   // (no integer round trip on this pointer: the compiler must keep seeing shared-space addresses,
   // or every access below turns into a generic LD.E / ST.E)
   extern __shared__ __align__(128) unsigned char smem_dyn[];
@@ -537,7 +557,7 @@ roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, const in
       const long long r = order ? (long long)order[i] : i;
       const int ti = n % kTabs;
       mbar_wait(&tab_empty[ti], (uint32_t)(((n / kTabs) & 1) ^ 1));  // (a fresh barrier passes)
-      const RoiPlace pl = build_rows_tab(lt, rois, r, tabs + ti, lane, &plan_scratch[p]);
+      const RoiPlace pl = build_rows_tab<kPxB>(lt, rois, r, tabs + ti, lane, &plan_scratch[p]);
       if (lane == 0) {
         tabs[ti].roi = (int)r;
         if (out_levels) out_levels[r] = pl.level;
@@ -545,7 +565,7 @@ roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, const in
       __syncwarp();
       // my turn: after planner p - 1 placed RoI n - 1 (planner 0's first turn is free)
       mbar_wait(&place_turn[p], (uint32_t)((k & 1) ^ (p == 0 ? 1 : 0)));
-      place_rows(tabs + ti, lane, &ring_state, full_a, idle_a);
+      place_rows<kPxB>(tabs + ti, lane, &ring_state, full_a, idle_a);
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&place_turn[(p + 1) % kPlanWarps]);
@@ -568,14 +588,15 @@ roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, const in
       if (nent > 0) {
         const int level = tb->level, width = tb->width;
         const char* gbase = reinterpret_cast<const char*>(lt.data[level]) +
-                            (size_t)tb->batch * lt.H[level] * width * kPxBytes;
+                            (size_t)tb->batch * lt.H[level] * width * kPxB;
         uint32_t my_pos = 0, my_len = 0;
         if (lane < nruns) {
-          my_pos = (uint32_t)tb->run_pos[lane] * kPxBytes;
-          my_len = (uint32_t)tb->run_len[lane] * kPxBytes;
-          gbase += (size_t)tb->run_col[lane] * kPxBytes;
+          my_pos = (uint32_t)tb->run_pos[lane] * kPxB;
+          my_len = (uint32_t)tb->run_len[lane] * kPxB;
+          gbase += (size_t)tb->run_col[lane] * kPxB;
         }
-        const uint32_t size = (uint32_t)ncols * kPxBytes;
+
+        const uint32_t size = (uint32_t)ncols * kPxB;
         // first entry of this RoI that belongs to this warp
         int e = (int)((cw + kCopyWarps - g0 % kCopyWarps) % kCopyWarps);
         for (; e < nent; e += kCopyWarps) {
@@ -585,7 +606,7 @@ roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, const in
           if (dep > 0) mbar_wait(&empty_bar[(dep - 1u) % kNBar], ((dep - 1u) / kNBar) & 1u);
           if (lane == 0) mbar_arrive_expect_tx(&full_bar[bi], size);
           if (lane < nruns)
-            bulk_g2s(ring + place + my_pos, gbase + (size_t)tb->ent_y[e] * width * kPxBytes, my_len, &full_bar[bi]);
+            bulk_g2s(ring + place + my_pos, gbase + (size_t)tb->ent_y[e] * width * kPxB, my_len, &full_bar[bi]);
         }
         g0 += (uint32_t)nent;
       }
@@ -603,7 +624,7 @@ roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, const in
   const int rot = (lane >> 3) & 3;
   // 32-bit shared addresses, pinned in registers (ptxas otherwise re-derives them from the CTA's
   // shared window at every use)
-  uint32_t ring_a = smem_u32(ring) + q * 16, tabs_a = smem_u32(tabs);
+  uint32_t ring_a = smem_u32(ring) + q * (kPxB / 64), tabs_a = smem_u32(tabs);
   uint32_t empty_off = smem_u32(empty_bar) - smem_u32(full_bar);
   // tile slots of the thread's four channels, rotated by lane / 8 so that the 32 lanes of a store hit
   // 32 different banks (thread stride 4 * 49 floats = 4 mod 32, channel stride 49 = 17 mod 32)
@@ -659,9 +680,9 @@ roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, const in
     const uint32_t c0 = ring_a + cxv.x, c1 = ring_a + cxv.y, c2 = ring_a + cxv.z, c3 = ring_a + cxv.w;
     const uint32_t ent_a = tb_a + (uint32_t)offsetof(RoiTab, ent), gend_a = tb_a + (uint32_t)offsetof(RoiTab, gend);
     // (nk is the same for the whole warp: one specialised loop per RoI, no per-entry branches)
-    if (nk > 3) consume_roi<4, kProbe>(ent_a, gend_a, c0, c1, c2, c3, wxv, empty_off, lane, flush);
-    else if (nk > 2) consume_roi<3, kProbe>(ent_a, gend_a, c0, c1, c2, c3, wxv, empty_off, lane, flush);
-    else consume_roi<2, kProbe>(ent_a, gend_a, c0, c1, c2, c3, wxv, empty_off, lane, flush);
+    if (nk > 3) consume_roi<4, kProbe, kPxB>(ent_a, gend_a, c0, c1, c2, c3, wxv, empty_off, lane, flush);
+    else if (nk > 2) consume_roi<3, kProbe, kPxB>(ent_a, gend_a, c0, c1, c2, c3, wxv, empty_off, lane, flush);
+    else consume_roi<2, kProbe, kPxB>(ent_a, gend_a, c0, c1, c2, c3, wxv, empty_off, lane, flush);
     // the tables of this RoI are no longer needed
     __syncwarp();
     if (lane == 0) mbar_arrive(&tab_empty[ti]);
@@ -670,7 +691,7 @@ roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, const in
     // bulk store (TMA) that drains while the consumers are already in the next RoI's rows ----
     fence_proxy_async();  // this thread's tile writes -> visible to the async proxy
     bar_consumers<kConsThreads>();
-    if (tid == 0) bulk_s2g(out + (size_t)r * kTileFloats, smem_u32(tile), kTileFloats * 4, store_policy);
+    if (tid == 0 && !(flags & 1)) bulk_s2g(out + (size_t)r * kTileFloats, smem_u32(tile), kTileFloats * 4, store_policy);
     if (out_mean && tid < kRC) {
       const float* row = tile + tid * kBins;
       float s = 0.f;
@@ -764,8 +785,8 @@ bool rows_kernel_applies(const LevelTable& lt, int C, int PH, int PW) {
 }
 
 // Preconditions (checked by the caller): NHWC, sampling_ratio 2; rows_kernel_applies().
-int launch_forward_rows(const LevelTable& lt, int C, const float* rois, int64_t n_rois, float* out, float* out_mean,
-                        int32_t* out_levels, int32_t* order_ws, int variant, cudaStream_t st) {
+int launch_forward_rows(const LevelTable& lt, int C, bool bf16_maps, const float* rois, int64_t n_rois, float* out,
+                        float* out_mean, int32_t* out_levels, int32_t* order_ws, int variant, cudaStream_t st) {
   B200_REQUIRE(C == kRC, "roi_align rows kernel: %d channels", C);
   B200_REQUIRE(n_rois < ((int64_t)1 << 31), "roi_align rows kernel: too many RoIs");
   // variant (tuning hook of b200_debug_set): bit 5 = visit the RoIs in the order given (no b200 ordering pass),
@@ -778,18 +799,23 @@ int launch_forward_rows(const LevelTable& lt, int C, const float* rois, int64_t 
     order = order_ws;
   }
   const int64_t grid = n_rois < sm_count() ? n_rois : sm_count();
-#define B200_ROWS(CW, PROBE)                                                                                    \
+#define B200_ROWS(CW, PROBE, PXB)                                                                               \
   do {                                                                                                          \
     static SmemHighWater hw;                                                                                    \
-    int rc = ensure_dynamic_smem(roi_align_fwd_rows<CW, PROBE>, kRowsSmem, &hw, "roi_align rows: smem");        \
+    int rc = ensure_dynamic_smem(roi_align_fwd_rows<CW, PROBE, PXB>, kRowsSmem, &hw, "roi_align rows: smem");   \
     if (rc != B200_OK) return rc;                                                                               \
-    roi_align_fwd_rows<CW, PROBE><<<(unsigned)grid, 32 * kConsWarps + 32 * kPlanWarps + 32 * CW, kRowsSmem, st>>>( \
-        lt, rois, order, (long long)n_rois, out, out_mean, out_levels);                                         \
+    roi_align_fwd_rows<CW, PROBE, PXB><<<(unsigned)grid, 32 * kConsWarps + 32 * kPlanWarps + 32 * CW, kRowsSmem, st>>>( \
+        lt, rois, order, (long long)n_rois, out, out_mean, out_levels, (variant >> 8) & 1);                     \
   } while (0)
   // (L2 prefetch of the planned rows -- bulk prefetches from the planner or one RoI ahead from a copy warp,
   // and LSU-side prefetch.global.L2 -- was measured 10-45 % SLOWER in all three forms: DESIGN.md)
-  if (variant & 64) B200_ROWS(2, 1);
-  else B200_ROWS(2, 0);
+  // bit 7 (tuning): two copy warps instead of four
+  if (bf16_maps) {
+    if (variant & 128) B200_ROWS(2, 0, kRC * 2);
+    else B200_ROWS(4, 0, kRC * 2);
+  } else if (variant & 64) B200_ROWS(4, 1, kRC * 4);
+  else if (variant & 128) B200_ROWS(2, 0, kRC * 4);
+  else B200_ROWS(4, 0, kRC * 4);
 #undef B200_ROWS
   B200_CHECK_LAUNCH("roi_align_fwd_rows");
   return B200_OK;

@@ -60,8 +60,10 @@ def _check_inputs(feats, rois):
         raise ValueError("need 1..%d feature levels" % _ext.B200_MAX_LEVELS)
     for f in feats:
         _ext.require_cuda(f, "input")
-        if f.dtype != torch.float32:
-            raise TypeError("input must be float32 (the reference forces fp32: layers/roi_align.py:57)")
+        if f.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+            raise TypeError("input must be float32, bfloat16 or float16")
+        if f.dtype != feats[0].dtype:
+            raise TypeError("all levels must share one dtype")
     _ext.require_cuda(rois, "rois")
     if rois.dim() != 2 or rois.size(1) != 5:
         raise ValueError("rois must be [R,5] (batch_index, x1, y1, x2, y2)")
@@ -93,6 +95,16 @@ def _forward(feats, scales, rois, output_size, sampling_ratio, want_levels=False
         raise ValueError("math must be one of %s" % (MATH_MODES,))
     ph, pw = output_size
     rois = rois.float().contiguous()
+    if feats[0].dtype != torch.float32:
+        # The reference computes RoIAlign in fp32 whatever the input precision (amp.float_function,
+        # layers/roi_align.py:57).  bf16 channels_last maps of the FPN box-pooler shape stay bf16 all the way
+        # into the kernel (b200_roi_align_forward_bf16: half the bytes, fp32 arithmetic and output); every other
+        # reduced-precision input is widened first, as the reference does.
+        out = _forward_bf16(feats, scales, rois, (ph, pw), sampling_ratio, want_levels, mean_out) \
+            if math == "fast" else None
+        if out is not None:
+            return out
+        feats = [f.float() for f in feats]
     lay = [_layout_of(f) for f in feats]
     layouts = {l for l, _ in lay}
     if len(layouts) > 1:  # mixed: fall back to the reference's layout for all
@@ -117,6 +129,32 @@ def _forward(feats, scales, rois, output_size, sampling_ratio, want_levels=False
                 MATH_MODES.index(math), _ext.ptr(out), _ext.ptr(mean_out), _ext.ptr(levels_out), _ext.ptr(ws),
                 ws.numel() if ws is not None else 0, _ext.stream_ptr(dev))
         _ext.check(rc, "b200_roi_align_forward")
+    return out, levels_out
+
+
+def _forward_bf16(feats, scales, rois, output_size, sampling_ratio, want_levels, mean_out):
+    """bf16 maps straight into the row-streaming kernel, or None when the shape has no bf16 kernel."""
+    ph, pw = output_size
+    if feats[0].dtype != torch.bfloat16 or (ph, pw) != (7, 7) or sampling_ratio != 2 or feats[0].size(1) != 256:
+        return None
+    if any(_layout_of(f)[0] != _ext.B200_LAYOUT_NHWC for f in feats):
+        return None
+    r, c = rois.size(0), 256
+    dev = feats[0].device
+    out = torch.empty((r, c, ph, pw), dtype=torch.float32, device=dev)
+    levels_out = torch.empty((r,), dtype=torch.int32, device=dev) if want_levels else None
+    if r > 0:
+        if mean_out is not None and (mean_out.shape != (r, c) or mean_out.dtype != torch.float32 or
+                                     not mean_out.is_contiguous() or mean_out.device != dev):
+            raise ValueError("mean_out must be a contiguous float32 [R,C] tensor on the input's device")
+        lib = _ext.lib()
+        arr = _levels_array(feats, scales)
+        ws = _workspace(lib.b200_roi_align_workspace_bytes(r), dev)
+        with torch.cuda.device(dev):
+            rc = lib.b200_roi_align_forward_bf16(arr, len(feats), _ext.B200_LAYOUT_NHWC, feats[0].size(0), c, _ext.ptr(rois), r,
+                                                 ph, pw, 2, _ext.ptr(out), _ext.ptr(mean_out), _ext.ptr(levels_out),
+                                                 _ext.ptr(ws), ws.numel(), _ext.stream_ptr(dev))
+        _ext.check(rc, "b200_roi_align_forward_bf16")
     return out, levels_out
 
 
@@ -177,7 +215,7 @@ nhwc_cache = _NhwcCache()
 
 def _stageable(f, sampling_ratio):
     """NCHW-contiguous CUDA map that the marching kernels could take if it were NHWC."""
-    return (f.is_cuda and f.dim() == 4 and sampling_ratio == 2 and f.size(1) % 64 == 0 and f.size(1) > 1 and
+    return (f.is_cuda and f.dtype == torch.float32 and f.dim() == 4 and sampling_ratio == 2 and f.size(1) % 64 == 0 and f.size(1) > 1 and
             f.is_contiguous() and not f.is_contiguous(memory_format=torch.channels_last))
 
 
@@ -193,6 +231,9 @@ class _ROIAlignMulti(Function):
         staged = [bool(stage) and _stageable(f, sampling_ratio) for f in feats]
         run = [nhwc_cache.get(f) if s else f for f, s in zip(feats, staged)]
         out, _ = _forward(run, scales, rois, output_size, sampling_ratio, math=math)
+        ctx.in_dtype = feats[0].dtype if feats else torch.float32
+        if ctx.in_dtype != torch.float32:
+            out = out.to(ctx.in_dtype)     # the Pooler hands back the input dtype (reference poolers.py:104-109)
         ctx.save_for_backward(rois.float().contiguous())
         ctx.output_size = output_size
         ctx.scales = tuple(scales)
@@ -207,6 +248,7 @@ class _ROIAlignMulti(Function):
     @once_differentiable
     def backward(ctx, grad_output):
         (rois,) = ctx.saved_tensors
+        # (gradients are accumulated in fp32 -- atomics on the fp32 buffer -- and rounded once at the end)
         grads = _backward(grad_output, rois, ctx.shapes, ctx.nhwc, ctx.scales, ctx.output_size,
                           ctx.sampling_ratio)
         if ctx.nhwc and any(ctx.staged):
@@ -223,6 +265,8 @@ class _ROIAlignMulti(Function):
                     g = n
                 out.append(g)
             grads = out
+        if ctx.in_dtype != torch.float32:
+            grads = [g.to(ctx.in_dtype) for g in grads]
         return (None, None, None, None, None, None, *grads)
 
 

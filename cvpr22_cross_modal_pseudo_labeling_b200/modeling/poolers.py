@@ -65,14 +65,11 @@ class Pooler(nn.Module):
         """x: list[Tensor [B,C,H_l,W_l]], boxes: list[BoxList] -> [R,C,PH,PW] in RoI order."""
         rois = self.convert_to_roi_format(boxes)
         feats = list(x)[: len(self.scales)]
-        dtype = feats[0].dtype
-        if dtype != torch.float32:
-            # the reference's ROIAlign runs under amp.float_function (layers/roi_align.py:57) and the Pooler
-            # stores the result in the input dtype (poolers.py:104-109): half / bf16 maps work the same here
-            feats = [f.float() for f in feats]
-        out = roi_align_multilevel(feats, rois.float(), self.output_size, self.scales, self.sampling_ratio,
-                                   stage_nhwc=self.stage_nhwc, math=self.math)
-        return out if dtype == torch.float32 else out.to(dtype)
+        # half / bf16 maps: the op computes in fp32 (the reference's amp.float_function, layers/roi_align.py:57)
+        # and the result comes back in the input dtype (poolers.py:104-109); layers.roi_align handles both,
+        # keeping bf16 channels_last maps of the box-pooler shape bf16 all the way into the kernel
+        return roi_align_multilevel(feats, rois.float(), self.output_size, self.scales, self.sampling_ratio,
+                                    stage_nhwc=self.stage_nhwc, math=self.math)
 
 
 def make_pooler(cfg, head_name):

@@ -137,6 +137,21 @@ int b200_roi_align_forward_ws(const b200_level* levels, int n_levels, int layout
                               size_t workspace_bytes, void* stream);
 
 /*
+ * The same forward on bf16 feature maps (levels[l].data points at bf16 values; BASELINE config #4: the
+ * bf16 training step): the maps are read as bf16 -- half the bytes through the copy ring -- widened to fp32
+ * in registers, pooled with the fast-math arithmetic, and written as fp32.  That is the reference's
+ * amp.float_function (layers/roi_align.py:57: the op computes in fp32 whatever the input precision) on
+ * bf16-rounded inputs.  Only the row-streaming shape has a bf16 kernel (NHWC, 256 channels, 7x7 bins,
+ * sampling ratio 2); anything else returns B200_ERR_UNSUPPORTED and the caller casts to fp32.
+ */
+int b200_roi_align_forward_bf16(const b200_level* levels, int n_levels, int layout,
+                                int batch, int channels, const float* rois,
+                                int64_t n_rois, int pooled_h, int pooled_w,
+                                int sampling_ratio, float* out, float* out_mean,
+                                int32_t* out_levels, void* workspace,
+                                size_t workspace_bytes, void* stream);
+
+/*
  * Fused multi-level RoIAlign backward (gradient w.r.t. the features).
  * Replaces _C.roi_align_backward (csrc/ROIAlign.h:27-45; kernel
  * csrc/cuda/ROIAlign_cuda.cu:178-254, host :302-346) for every level at once.

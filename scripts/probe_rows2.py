@@ -50,3 +50,14 @@ for name, rois in (("microbench", micro), ("bench step", step_rois)):
         print("%-10s variant %2d: %.3f ms (min %.3f; with mean %.3f)  %.0f GB/s = %.3f of 6548.5" %
               (name, v, t, tmin, tm, algo / t / 1e6, algo / t / 1e6 / 6548.5), flush=True)
 _ext.debug_set(False, True, 0)
+# bf16 maps (config #4): same RoIs, half the bytes through the ring
+fb = [f.to(torch.bfloat16).contiguous(memory_format=torch.channels_last) for f in feats]
+for name, rois in (("microbench", micro), ("bench step", step_rois)):
+    _, lv = _forward(fb, synth.FPN_SCALES, rois, (7, 7), 2, want_levels=True, math="fast")
+    ft = bench.f_touched_bytes(rois, lv, shapes, synth.FPN_SCALES, C) // 2
+    algo = ft + rois.shape[0] * (C * 49 * 4 + 20)
+    for v in variants:
+        _ext.debug_set(False, True, v)
+        t, tmin = timeit(lambda: _forward(fb, synth.FPN_SCALES, rois, (7, 7), 2, math="fast"))
+        print("%-10s bf16 maps variant %4d: %.3f ms (min %.3f)  %.0f GB/s = %.3f of 6548.5" % (name, v, t, tmin, algo / t / 1e6, algo / t / 1e6 / 6548.5), flush=True)
+_ext.debug_set(False, True, 0)
