@@ -863,6 +863,120 @@ def run_gpu(args):
     return 0
 
 
+def run_train(args):
+    """BASELINE config #4: one student training step of the RoI path in bf16 -- box pooler forward + backward on
+    512 sampled RoIs per image (ROI_HEADS.BATCH_SIZE_PER_IMAGE, config/defaults.py:282) and the embedding head
+    (fc stand-in, emb_pred, class scoring) forward + backward on the tensor cores -- with the head gradients
+    all-reduced over NCCL as DDP does (tools/train_net.py:65-71).  Prints one JSON line (not the headline metric)."""
+    import torch
+    import torch.distributed as dist
+    from cvpr22_cross_modal_pseudo_labeling_b200 import _ext
+    from cvpr22_cross_modal_pseudo_labeling_b200.layers import TensorCoreLinear, embed_logits, roi_align_multilevel
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _ext.lib()
+    r_img = 512
+    seed = 1238 + 1000 * rank
+    rng = np.random.default_rng(seed)
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    shapes, scales = synth.fpn_shapes(), synth.FPN_SCALES
+    feats = [torch.randn((B_IMG, h, w, C_FEAT), device=dev, generator=gen).to(torch.bfloat16).permute(0, 3, 1, 2).requires_grad_(True)
+             for (h, w) in shapes]
+    rois = torch.from_numpy(synth.make_rois(rng, r_img, B_IMG)).to(dev)
+    n = rois.shape[0]
+    labels = torch.randint(0, N_CLASSES, (n,), device=dev, generator=gen)
+    E = torch.nn.functional.normalize(torch.randn((N_CLASSES, EMB_DIM), device=dev, generator=gen), dim=-1)
+    E[0] = 0
+    E = E.to(torch.bfloat16)
+    torch.manual_seed(1238)     # same initial head on every rank
+    fc = TensorCoreLinear(C_FEAT, HEAD_DIM).to(dev)
+    emb_pred = TensorCoreLinear(HEAD_DIM, EMB_DIM).to(dev)
+    params = list(fc.parameters()) + list(emb_pred.parameters())
+    flat = torch.zeros((sum(p.numel() for p in params),), device=dev)
+
+    def step():
+        for f in feats:
+            f.grad = None
+        for p_ in params:
+            p_.grad = None
+        pooled = roi_align_multilevel(feats, rois, (7, 7), scales, 2, math="fast")          # bf16 in, bf16 out
+        x = pooled.mean(dim=(2, 3))
+        hid = torch.relu(fc(x))
+        emb = emb_pred(hid)
+        logits = embed_logits(emb, E)
+        loss = torch.nn.functional.cross_entropy(logits.float(), labels)
+        loss.backward()
+        if world > 1:      # DDP-style: one all-reduce of the flattened head gradients
+            torch.cat([p_.grad.reshape(-1) for p_ in params], out=flat)
+            dist.all_reduce(flat)
+        return loss
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        loss = step()
+    t1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    clocks = sampler.stop()
+    tms = torch.tensor([t0.elapsed_time(t1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms[0]) / args.steps
+    # per-stage device times (one extra pass)
+    ev = {}
+
+    def timed(name, fn):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = fn()
+        b.record()
+        b.synchronize()
+        ev[name] = a.elapsed_time(b)
+        return out
+    for f in feats:
+        f.grad = None
+    g = None
+    for _ in range(2):   # (the second pass is the one reported)
+        pooled = timed("pool7_fwd_bf16", lambda: roi_align_multilevel(feats, rois, (7, 7), scales, 2, math="fast"))
+        if g is None:
+            g = torch.randn(pooled.shape, device=dev, generator=gen).to(torch.bfloat16)
+            torch.cuda.synchronize()
+        timed("pool7_bwd_incl_casts_and_zero_fill", lambda: pooled.backward(g))
+    if rank == 0:
+        line = {"metric": "RoIs/sec trained (box pooler fwd+bwd + embedding head fwd+bwd), BASELINE config #4",
+                "value": world * n / (ms * 1e-3), "unit": "RoIs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic", "loss": float(loss.detach()),
+                "config": bench_config(workload="student training step of the RoI path: %d img/GPU x %d sampled RoIs, bf16 NHWC features, "
+                                                "4-level RoIAlign 7x7 fwd+bwd, fc(256->1024) + emb_pred(1024->768) + 66-class scoring fwd+bwd on "
+                                                "tcgen05, cross-entropy; head gradients all-reduced over NCCL" % (B_IMG, r_img),
+                                       rois_per_image=r_img, feature_layout="channels_last bf16", launch="eager autograd",
+                                       sample="%d images per GPU per step" % B_IMG),
+                "clocks": clocks, "stage_ms": ev, "gpu_launches": None}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -874,6 +988,8 @@ def main():
                          "BASELINE.json states); exact = the reference's operation order, bit-identical")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 4],
+                    help="2: the headline inference step (BASELINE configs #2/#3); 4: the bf16 student training step (config #4)")
     ap.add_argument("--same-seed", action="store_true", help="every rank draws the same synthetic batch")
     ap.add_argument("--sustain", type=float, default=2.0, help="seconds of back-to-back replay for the `sustained` record (0 = skip)")
     ap.add_argument("--no-roofline-all", action="store_true", help="skip the extra per-kernel roofline passes")
@@ -881,6 +997,8 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
+    if args.config == 4:
+        return run_train(args)
     return run_gpu(args)
 
 

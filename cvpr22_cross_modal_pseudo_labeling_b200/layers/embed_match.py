@@ -75,9 +75,23 @@ class _EmbedLogits(Function):
     @staticmethod
     def backward(ctx, grad_logits):
         cls_emb, E = ctx.saved_tensors
-        g = grad_logits.float()
-        g_emb = (g @ E.float()).to(cls_emb.dtype) if ctx.needs_input_grad[0] else None
-        g_E = (g.t() @ cls_emb.float()).to(E.dtype) if ctx.needs_input_grad[1] else None
+        g_emb = g_E = None
+        if ctx.needs_input_grad[0] and cls_emb.dtype == torch.float32:
+            g_emb = grad_logits.float() @ E.float()        # fp32 training keeps the fp32 product
+        elif ctx.needs_input_grad[0]:
+            # bf16 (AMP / config #4): grad_emb [R, D] = g [R, C] . E [C, D] on the tensor cores; the contraction
+            # runs over the C classes, padded to a multiple of 8 (16-byte rows for TMA)
+            from .linear import linear_bf16
+            c = grad_logits.shape[1]
+            pad = (-c) % 8
+            g16 = grad_logits.to(torch.bfloat16)
+            et = E.detach().to(torch.bfloat16).t()
+            if pad:
+                g16 = torch.nn.functional.pad(g16, (0, pad))
+                et = torch.nn.functional.pad(et, (0, pad))
+            g_emb = linear_bf16(g16.contiguous(), et.contiguous(), None)[0].to(cls_emb.dtype)
+        if ctx.needs_input_grad[1]:
+            g_E = (grad_logits.float().t() @ cls_emb.float()).to(E.dtype)
         return g_emb, g_E
 
 
