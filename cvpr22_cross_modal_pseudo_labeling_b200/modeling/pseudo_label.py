@@ -49,6 +49,8 @@ def pack_records(pseudo_labels, image_ids, w_max):
     [B, w_max, 8] fp32 tensor (img_id, label, x1, y1, x2, y2, score, region_idx) and a
     [B] int32 count -- what the ranks all-gather over NCCL."""
     dev = pseudo_labels[0].bbox.device if pseudo_labels else torch.device("cuda")
+    if any(abs(int(i)) >= (1 << 24) for i in image_ids):
+        raise ValueError("image ids must be below 2^24 (the record stores them as fp32)")
     rec = torch.zeros((len(pseudo_labels), w_max, 8), dtype=torch.float32, device=dev)
     cnt = torch.zeros((len(pseudo_labels),), dtype=torch.int32, device=dev)
     for i, pl in enumerate(pseudo_labels):

@@ -71,6 +71,9 @@ def save_records(path, records, counts, meta=None):
     meta_b = json.dumps(meta or {}, sort_keys=True).encode("utf-8")
     valid = np.arange(w_max)[None, :] < counts[:, None]
     rows = records[valid]  # image-major, [n_rows, n_fields]
+    # image_id, label_id and region_idx travel as fp32: exact only below 2^24
+    if rows.size and float(np.abs(rows[:, [0, 1, 7]]).max()) >= float(1 << 24):
+        raise ValueError("image_id / label_id / region_idx must be below 2^24 (they are stored as fp32)")
     tmp = path + ".tmp"
     with open(tmp, "wb") as f:
         f.write(_HEADER.pack(MAGIC, VERSION, n_images, w_max, n_fields, rows.shape[0], len(meta_b)))

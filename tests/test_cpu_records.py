@@ -165,3 +165,11 @@ def test_shard_files_merge_to_what_the_all_gather_returns_gloo(tmp_path):
                               stderr=subprocess.STDOUT, text=True) for r in range(2)]
     outs = [p.communicate(timeout=180)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+def test_ids_beyond_fp32_exactness_are_refused(tmp_path):
+    rec, cnt = _make(2, 3, 9)
+    cnt[:] = 3
+    rec[0, 0, 0] = float(1 << 24)
+    with pytest.raises(ValueError):
+        R.save_records(str(tmp_path / "x.b2pl"), rec, cnt)
