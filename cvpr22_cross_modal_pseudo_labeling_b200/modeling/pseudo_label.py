@@ -51,16 +51,20 @@ def pack_records(pseudo_labels, image_ids, w_max):
     dev = pseudo_labels[0].bbox.device if pseudo_labels else torch.device("cuda")
     if any(abs(int(i)) >= (1 << 24) for i in image_ids):
         raise ValueError("image ids must be below 2^24 (the record stores them as fp32)")
+    # one concatenation + one indexed store for the whole batch (no per-image device writes: at 64 images per
+    # GPU a loop of scalar assignments costs more than the kernels that produced the labels)
+    ns = [min(len(pl), w_max) for pl in pseudo_labels]
     rec = torch.zeros((len(pseudo_labels), w_max, 8), dtype=torch.float32, device=dev)
-    cnt = torch.zeros((len(pseudo_labels),), dtype=torch.int32, device=dev)
-    for i, pl in enumerate(pseudo_labels):
-        n = min(len(pl), w_max)
-        cnt[i] = n
+    cnt = torch.tensor(ns, dtype=torch.int32, device=dev)
+    rows, img_idx, slot_idx = [], [], []
+    for i, (pl, n) in enumerate(zip(pseudo_labels, ns)):
         if n == 0:
             continue
-        rec[i, :n, 0] = float(image_ids[i])
-        rec[i, :n, 1] = pl.get_field("labels")[:n].float()
-        rec[i, :n, 2:6] = pl.convert("xyxy").bbox[:n]
-        rec[i, :n, 6] = pl.get_field("scores")[:n]
-        rec[i, :n, 7] = pl.get_field("region_idx")[:n].float() if pl.has_field("region_idx") else -1.0
+        region = pl.get_field("region_idx")[:n].float() if pl.has_field("region_idx") else torch.full((n,), -1.0, device=dev)
+        rows.append(torch.cat([torch.full((n, 1), float(image_ids[i]), device=dev), pl.get_field("labels")[:n].float()[:, None],
+                               pl.convert("xyxy").bbox[:n], pl.get_field("scores")[:n][:, None], region[:, None]], dim=1))
+        img_idx += [i] * n
+        slot_idx += list(range(n))
+    if rows:
+        rec[torch.tensor(img_idx, device=dev), torch.tensor(slot_idx, device=dev)] = torch.cat(rows)
     return rec, cnt
