@@ -683,7 +683,11 @@ def run_gpu(args):
     # ~20 ms; this shows whether the number holds once clocks and power settle)
     sustained = None
     if args.sustain > 0:
-        n_sus = max(args.steps, int(args.sustain * 1e3 / max(ms_total / args.steps, 1e-3)))
+        # the step count must be the same on every rank (each replay issues one all-gather): agree on the slowest
+        ms_any = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms_any, op=dist.ReduceOp.MAX)
+        n_sus = max(args.steps, int(args.sustain * 1e3 / max(float(ms_any[0]) / args.steps, 1e-3)))
         sync_all()
         sampler2 = ClockSampler(local)
         sampler2.start()
