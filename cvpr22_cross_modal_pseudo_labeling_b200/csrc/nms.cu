@@ -414,31 +414,85 @@ nms_fused_kernel(const float4* __restrict__ boxes, const float* __restrict__ sco
   for (int c0 = 0; c0 < n && !done; c0 += chunk_boxes) {
     const int c1 = min(n, c0 + chunk_boxes);
     if (can_stop) {
-      // this chunk's boxes in x-centre order
+      // this chunk's boxes in x-centre order: a counting sort into 256 x buckets between the chunk's
+      // smallest and largest centre (histogram with shared atomics, one scan, one scatter: 4 barriers; the
+      // bitonic sort of the 1024 keys it replaces took 55).  The order inside a bucket is whatever the
+      // atomics give -- it only decides which lane tests which box, never a verdict.
       const int clen = c1 - c0;
-      for (int t = tid; t < kChunkBoxes; t += kThreads) {
-        u64 key = ~0ull;
-        if (t < clen) {
-          const float4 b = sb[c0 + t];
-          key = ((u64)orderable_f(0.5f * (b.x + b.z)) << 32) | (uint32_t)t;
-        }
-        pkeys[t] = key;
+      constexpr int kPer = (kChunkBoxes + kThreads - 1) / kThreads;
+      int* bcnt = reinterpret_cast<int*>(pkeys);  // 256 counters, then their exclusive scan (pkeys is free here)
+      int* brange = bcnt + 256;                    // orderable(min cx), orderable(max cx)
+      if (tid < 256) bcnt[tid] = 0;
+      if (tid == 0) {
+        brange[0] = 0x7fffffff;
+        brange[1] = (int)0x80000000;
       }
       __syncthreads();
-      for (int k = 2; k <= kChunkBoxes; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-          for (int t = tid; t < (kChunkBoxes >> 1); t += kThreads) {
-            const int lo = 2 * t - (t & (j - 1)), hi = lo + j;
-            const u64 a = pkeys[lo], b = pkeys[hi];
-            if ((a > b) == ((lo & k) == 0)) {
-              pkeys[lo] = b;
-              pkeys[hi] = a;
-            }
+      float cxs[kPer];
+      {
+        int mn = 0x7fffffff, mx = (int)0x80000000;
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+          const int t = tid + k * kThreads;
+          cxs[k] = 0.f;
+          if (t < clen) {
+            const float4 b = sb[c0 + t];
+            cxs[k] = 0.5f * (b.x + b.z);
+            const int o = (int)(orderable_f(cxs[k]) ^ 0x80000000u);  // signed-orderable
+            mn = min(mn, o);
+            mx = max(mx, o);
           }
-          __syncthreads();
+        }
+        mn = __reduce_min_sync(0xffffffffu, mn);
+        mx = __reduce_max_sync(0xffffffffu, mx);
+        if (lane == 0) {
+          atomicMin(&brange[0], mn);
+          atomicMax(&brange[1], mx);
         }
       }
-      for (int t = tid; t < kChunkBoxes; t += kThreads) perm[t] = (int)(uint32_t)pkeys[t];  // -1: padding
+      __syncthreads();
+      int bkt[kPer], slot[kPer];
+      {
+        const uint32_t umn = (uint32_t)brange[0] ^ 0x80000000u, umx = (uint32_t)brange[1] ^ 0x80000000u;
+        const float lo = __uint_as_float((umn & 0x80000000u) ? (umn & 0x7fffffffu) : ~umn);
+        const float hi = __uint_as_float((umx & 0x80000000u) ? (umx & 0x7fffffffu) : ~umx);
+        const float scale = hi > lo ? 255.999f / (hi - lo) : 0.f;
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+          const int t = tid + k * kThreads;
+          bkt[k] = -1;
+          if (t < clen) {
+            bkt[k] = min(255, max(0, (int)((cxs[k] - lo) * scale)));
+            slot[k] = atomicAdd(&bcnt[bkt[k]], 1);
+          }
+        }
+      }
+      __syncthreads();
+      if (tid < 32) {  // exclusive scan of the 256 counters by one warp (8 per lane)
+        int c[8], run = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          c[j] = bcnt[8 * tid + j];
+          run += c[j];
+        }
+        int incl = run;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += v;
+        }
+        int ex = incl - run;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          bcnt[8 * tid + j] = ex;
+          ex += c[j];
+        }
+      }
+      for (int t = clen + tid; t < kChunkBoxes; t += kThreads) perm[t] = -1;  // padding
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < kPer; ++k)
+        if (bkt[k] >= 0) perm[bcnt[bkt[k]] + slot[k]] = tid + k * kThreads;
       __syncthreads();
       if (c0 > 0 && nk > 0) {
         // chunk vs everything kept so far
