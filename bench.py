@@ -405,6 +405,29 @@ def roofline_passes(torch, dev, feats, scales, shapes, state, cand_boxes, cand_s
         out.append(hbm_entry("roi_align bwd %dx%d (incl. zero fill of the gradient pyramid)" % (res, res),
                              n * (C_FEAT * res * res * 4 + 20) + f_all, ms, rois=int(n)))
         del g
+    # BASELINE config #1, the reference's shipped pooler: C4 map [1, 1024, 50, 84] NCHW, 14x14 bins, adaptive
+    # sampling (sampling_ratio 0), scale 1/16, 1000 RoIs (config/defaults.py:301-305) -- exact arithmetic, both layouts
+    try:
+        gen1 = torch.Generator(device=dev).manual_seed(1235)
+        c4 = torch.randn((1, 1024, 50, 84), device=dev, generator=gen1)
+        r1 = torch.from_numpy(synth.make_rois(np.random.default_rng(1235), 1000, 1)).to(dev)
+        flush = torch.empty((256 << 20,), dtype=torch.uint8, device=dev)    # the 17 MB map would sit in the L2
+        for layout, x in (("NCHW (the reference's layout)", c4), ("channels_last", c4.contiguous(memory_format=torch.channels_last))):
+            ts = []
+            for _ in range(5):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                _forward([x], (1.0 / 16,), r1, (14, 14), 0, math="exact")
+                b.record()
+                b.synchronize()
+                ts.append(a.elapsed_time(b))
+            ms = float(np.median(ts[1:]))
+            out.append(hbm_entry("roi_align fwd config #1: C4 1024 ch, 14x14, sampling_ratio 0, 1000 RoIs, %s, exact" % layout,
+                                 c4.numel() * 4 + 1000 * (1024 * 196 * 4 + 20), ms, rois=1000, l2="flushed between iterations"))
+        del c4, flush
+    except Exception as e:
+        out.append({"kernel": "roi_align fwd config #1", "error": "%s: %s" % (type(e).__name__, e)})
     # RPN NMS: 80 segments, keep <= 1000 (pairwise-IoU tests are data dependent: boxes/s and the bitmask convention)
     lens = np.array(RPN_LENS * B_IMG, dtype=np.float64)
     ms = timeit(lambda: nms_batched(cand_boxes, cand_scores, seg_off, 0.7, 1000, max(RPN_LENS)))

@@ -426,9 +426,19 @@ extern "C" int b200_embed_match_wide(const void* A_bf16, const void* E_bf16, int
   using namespace b200;
   B200_REQUIRE(n_rows >= 0 && n_cols >= 0 && dim > 0, "embed_match_wide: bad shape");
   if (n_rows == 0 || n_cols == 0) return B200_OK;
-  B200_REQUIRE(logits, "embed_match_wide: the [n_rows, n_cols] logits buffer is required (output and scratch)");
   B200_REQUIRE(A_bf16 && E_bf16 && dim % 8 == 0, "embed_match_wide: null operand or dim %% 8 != 0");
-  // logits by column blocks of <= 512 (one TMEM allocation each), written at the full row pitch
+  B200_REQUIRE(aligned16(A_bf16) && aligned16(E_bf16), "embed_match_wide: operands must be 16-byte aligned");
+  B200_REQUIRE(n_rows < ((int64_t)1 << 31), "embed_match_wide: n_rows must fit int32 TMA coordinates");
+  if (!g_match_legacy) {
+    // one persistent launch: statistics pass + probability pass over recomputed blocks, the logits make no
+    // HBM round trip (tc_gemm.cu, SOFTMAX_WIDE); `logits` is an optional output, no longer scratch
+    if (!probs && !logits && !top_label) return B200_OK;
+    return softmax_wide_launch(A_bf16, E_bf16, n_rows, n_cols, dim, score_thresh, probs, logits, top_label, top_prob,
+                               static_cast<cudaStream_t>(stream));
+  }
+  // legacy (test hook b200_debug_match): logits by column blocks of <= 512 written at the full row pitch, then
+  // a row-softmax pass over them
+  B200_REQUIRE(logits, "embed_match_wide (legacy path): the [n_rows, n_cols] logits buffer is required (output and scratch)");
   for (int c0 = 0; c0 < n_cols; c0 += 512) {
     const int nb = n_cols - c0 < 512 ? n_cols - c0 : 512;
     const char* eb = static_cast<const char*>(E_bf16) + (size_t)c0 * dim * 2;

@@ -72,9 +72,10 @@ struct GemmParams {
   int32_t* top_label;
   float* top_prob;
   int ld;
+  int passes;  // SOFTMAX_WIDE: 2 (statistics, then probabilities) or 1 (no probabilities wanted)
 };
 
-enum { kEpiLinear = 0, kEpiSoftmax = 1 };
+enum { kEpiLinear = 0, kEpiSoftmax = 1, kEpiSoftmaxWide = 2 };
 
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile(
@@ -176,12 +177,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   // (row tile, column block) units one by one -- 500 tiles x 3 blocks over 148 CTAs is 10.1 units each,
   // whole row tiles would be 3.4 (one CTA in three does a fourth: 84 % at best)
   const long long n_outer = EPI == kEpiLinear ? n_mtiles * p.nblk : n_mtiles;
-  const int n_inner = EPI == kEpiLinear ? 1 : p.nblk;
+  // SOFTMAX_WIDE (more than two column blocks: the parked-block scheme would need all of them in shared
+  // memory): every row tile is multiplied TWICE -- pass 0 leaves only the row statistics, pass 1 recomputes
+  // the blocks and writes probabilities.  The [M, N] logits make no HBM round trip (the first version of the
+  // wide path wrote them, read them back in a softmax kernel and wrote the probabilities: 12 bytes per
+  // element; now 4, or 8 when the caller also wants the logits), at twice the tensor work of a class matrix
+  // that is wide but not tall.
+  const int n_inner = EPI == kEpiLinear ? 1 : EPI == kEpiSoftmax ? p.nblk : p.passes * p.nblk;
   // dynamic shared memory may start at any 16-byte boundary: realign for the 128 B swizzle
   unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~uintptr_t(1023));
   // SOFTMAX only: fp16 stash of e = exp(l - max), row statistics, per-warp transpose tiles for the logits
   unsigned char* stash = tiles + (size_t)p.stages * p.stage_bytes;
-  SoftStats* stats = reinterpret_cast<SoftStats*>(stash + kBM * kStashPitch);
+  SoftStats* stats = reinterpret_cast<SoftStats*>(stash + (EPI == kEpiSoftmax ? kBM * kStashPitch : 0));
   float* xpose = reinterpret_cast<float*>(stats + 1);
 
   if (threadIdx.x == 0) {
@@ -217,7 +224,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (long long o = blockIdx.x; o < n_outer; o += gridDim.x)
         for (int in = 0; in < n_inner; ++in) {
           const long long mt = EPI == kEpiLinear ? o / p.nblk : o;
-          const int blk = EPI == kEpiLinear ? (int)(o % p.nblk) : in;
+          const int blk = EPI == kEpiLinear ? (int)(o % p.nblk) : in % p.nblk;
           for (int kb = 0; kb < num_kb; ++kb, ++it) {
             const int s = it % p.stages;
             const uint32_t ph = (it / p.stages) & 1;
@@ -234,7 +241,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       uint32_t it = 0, j = 0;
       for (long long o = blockIdx.x; o < n_outer; o += gridDim.x)
         for (int in = 0; in < n_inner; ++in, ++j) {
-          const int blk = EPI == kEpiLinear ? (int)(o % p.nblk) : in;
+          const int blk = EPI == kEpiLinear ? (int)(o % p.nblk) : in % p.nblk;
           const int buf = j & 1;
           mbar_wait_park(&acc_empty[buf], ((j >> 1) & 1) ^ 1);  // the epilogue has drained this buffer
           tc_fence_after();
@@ -267,8 +274,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const long long mt = EPI == kEpiLinear ? o / p.nblk : o;
       const long long row = mt * kBM + trow;
       const bool row_ok = row < p.M;
+      // SOFTMAX_WIDE: running statistics of this thread's part of the row over the blocks of pass 0, then the
+      // row's maximum (x log2 e) and 1 / sum for pass 1
+      float w_rm = -INFINITY, w_rs = 0.f, w_best = -INFINITY, w_bg = -INFINITY, w_moff = 0.f, w_inv = 0.f;
+      int w_bestc = 0;
       for (int in = 0; in < n_inner; ++in, ++j) {
-        const int blk = EPI == kEpiLinear ? (int)(o % p.nblk) : in;
+        const int blk = EPI == kEpiLinear ? (int)(o % p.nblk) : in % p.nblk;
         const int buf = j & 1;
         const int col0 = blk * p.BN;
         const int bn = min(p.BN, NP - col0);
@@ -324,6 +335,102 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        } else if (EPI == kEpiSoftmaxWide) {
+          const int pass = in / p.nblk;
+          // logits / probabilities leave through a warp-private transpose tile: half a warp writes 64
+          // contiguous bytes of one row (2 rows per store instruction), whatever the row pitch
+          float* tt = xpose + (warp - kFirstEpiWarp) * (32 * 17);
+          const int rsub = lane >> 4, csub = lane & 15;
+          auto store_chunk = [&](float* outp, int c) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) tt[lane * 17 + i] = v[i];
+            __syncwarp();
+#pragma unroll 4
+            for (int rr = 0; rr < 32; rr += 2) {
+              const long long orow = mt * kBM + quad * 32 + rr + rsub;
+              if (orow < p.M && c + csub < p.N) outp[orow * p.ld + c + csub] = tt[(rr + rsub) * 17 + csub];
+            }
+            __syncwarp();
+          };
+          if (pass == 0) {
+            for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+              tmem_ld16(taddr + c0, v);
+              const int c = col0 + c0;
+              if (p.logits) store_chunk(p.logits, c);
+              if (c + 16 > p.N) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  if (c + i >= p.N) v[i] = -INFINITY;
+              }
+              if (c == 0) {
+                w_bg = v[0];
+                v[0] = -INFINITY;
+              }
+              const float before = w_best;
+              int bi = 0;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                bi = v[i] > w_best ? i : bi;
+                w_best = fmaxf(w_best, v[i]);
+              }
+              w_bestc = w_best > before ? c + bi : w_bestc;
+              if (c == 0) v[0] = w_bg;   // the background logit counts in the sum
+              const float nm = fmaxf(w_rm, fmaxf(w_best, w_bg));
+              if (nm > w_rm) {           // the running sum follows the running maximum
+                w_rs *= ex2_approx((w_rm - nm) * kLog2e);
+                w_rm = nm;
+              }
+              const float moff = w_rm * kLog2e;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) w_rs += ex2_approx(fmaf(v[i], kLog2e, -moff));
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            if (blk == p.nblk - 1) {
+              // the four parts of the row -> its maximum, 1 / sum and top-1 foreground label
+              stats->sum[0][ch][trow] = w_rs;
+              stats->sum[1][ch][trow] = w_rm;
+              stats->best[0][ch][trow] = w_best;
+              stats->best[1][ch][trow] = __int_as_float(w_bestc);
+              bar_named(1 + quad, 32 * kCH);
+              float rmx = -INFINITY;
+#pragma unroll
+              for (int h = 0; h < kCH; ++h) rmx = fmaxf(rmx, stats->sum[1][h][trow]);
+              float tot = 0.f;
+#pragma unroll
+              for (int h = 0; h < kCH; ++h) tot += stats->sum[0][h][trow] * ex2_approx((stats->sum[1][h][trow] - rmx) * kLog2e);
+              w_moff = rmx * kLog2e;
+              w_inv = 1.0f / tot;
+              if (ch == 0 && row_ok && p.top_label) {
+                float bb = -INFINITY;
+                int bc = 0;
+#pragma unroll
+                for (int h = 0; h < kCH; ++h)
+                  if (stats->best[0][h][trow] > bb) {   // parts in column order per block; see below for blocks
+                    bb = stats->best[0][h][trow];
+                    bc = __float_as_int(stats->best[1][h][trow]);
+                  } else if (stats->best[0][h][trow] == bb && __float_as_int(stats->best[1][h][trow]) < bc) {
+                    bc = __float_as_int(stats->best[1][h][trow]);   // equal maxima: the lower column wins
+                  }
+                const float bp = p.N > 1 ? ex2_approx(fmaf(bb, kLog2e, -w_moff)) * w_inv : 0.f;
+                p.top_label[row] = (p.N > 1 && bp > p.score_thresh) ? bc : 0;
+                if (p.top_prob) p.top_prob[row] = bp;
+              }
+              bar_named(1 + quad, 32 * kCH);   // the statistics may be overwritten by the next row tile
+              w_rm = -INFINITY, w_rs = 0.f, w_best = -INFINITY, w_bg = -INFINITY, w_bestc = 0;
+            }
+          } else {
+            for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+              tmem_ld16(taddr + c0, v);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = ex2_approx(fmaf(v[i], kLog2e, -w_moff)) * w_inv;
+              store_chunk(p.probs, col0 + c0);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+          }
         } else {
           const bool last = blk == p.nblk - 1;
           // ---- sweep A: row max and best foreground column (>= 1; first maximum wins) over my columns:
@@ -613,6 +720,23 @@ int softmax_gemm_launch(const void* A_bf16, const void* E_bf16, int64_t n_rows, 
   p.ld = ld;
   const size_t extra = sizeof(SoftStats) + 16 + (size_t)kBM * kStashPitch + (logits ? sizeof(float) * kEpiWarps * 32 * 17 : 0);
   return launch<kEpiSoftmax>(p, A_bf16, E_bf16, extra, st);
+}
+
+int softmax_wide_launch(const void* A_bf16, const void* E_bf16, int64_t n_rows, int n_cols, int dim, float score_thresh,
+                        float* probs, float* logits, int32_t* top_label, float* top_prob, cudaStream_t st) {
+  GemmParams p = {};
+  p.M = n_rows;
+  p.N = n_cols;
+  p.K = dim;
+  p.score_thresh = score_thresh;
+  p.probs = probs;
+  p.logits = logits;
+  p.top_label = top_label;
+  p.top_prob = top_prob;
+  p.ld = n_cols;
+  p.passes = probs ? 2 : 1;
+  const size_t extra = sizeof(SoftStats) + 16 + sizeof(float) * kEpiWarps * 32 * 17;
+  return launch<kEpiSoftmaxWide>(p, A_bf16, E_bf16, extra, st);
 }
 
 }  // namespace b200

@@ -34,9 +34,9 @@ def embed_match_softmax(A, E, score_thresh=0.05, want_probs=True, want_logits=Fa
         raise ValueError("A and E must share the embedding dimension")
     dev = A.device
     out = {}
-    wide = c > MAX_COLS   # column blocks + a row-softmax pass (b200_embed_match_wide); needs the logits buffer
+    wide = c > MAX_COLS   # b200_embed_match_wide: statistics pass + probability pass, no logits round trip
     probs = torch.empty((r, c), dtype=torch.float32, device=dev) if want_probs else None
-    logits = torch.empty((r, c), dtype=torch.float32, device=dev) if (want_logits or wide) else None
+    logits = torch.empty((r, c), dtype=torch.float32, device=dev) if want_logits else None
     top_label = torch.empty((r,), dtype=torch.int32, device=dev) if want_top else None
     top_prob = torch.empty((r,), dtype=torch.float32, device=dev) if want_top else None
     if r > 0 and c > 0 and wide:
@@ -45,8 +45,6 @@ def embed_match_softmax(A, E, score_thresh=0.05, want_probs=True, want_logits=Fa
                                                   _ext.ptr(probs), _ext.ptr(logits), _ext.ptr(top_label),
                                                   _ext.ptr(top_prob), _ext.stream_ptr(dev))
         _ext.check(rc, "b200_embed_match_wide")
-        if not want_logits:
-            logits = None
     elif r > 0 and c > 0:
         with torch.cuda.device(dev):
             rc = _ext.lib().b200_embed_match(_ext.ptr(A), _ext.ptr(E), r, c, d, _ext.B200_MATCH_SOFTMAX,

@@ -280,10 +280,11 @@ int b200_linear_bf16(const void* A_bf16, const void* W_bf16, const float* bias,
 
 /*
  * SOFTMAX scoring against a class matrix of ANY width (e.g. the 1203-word LVIS vocabulary the
- * student scores caption images against, detector/st_generalized_rcnn.py:71-75,:191): logits are
- * produced by column blocks of <= 512 on the tensor cores straight into the caller's
- * [n_rows, n_cols] logits buffer (required: output and scratch), then one row-softmax pass fills
- * probs / top_label / top_prob (each optional) with the semantics of b200_embed_match.
+ * student scores caption images against, detector/st_generalized_rcnn.py:71-75,:191): one persistent
+ * launch multiplies every 128-row tile twice -- a statistics pass (row max, sum, top-1 label), then a pass
+ * that recomputes the column blocks and writes the probabilities -- so the [n_rows, n_cols] logits make no
+ * HBM round trip.  probs / logits / top_label / top_prob are each optional, with the semantics of
+ * b200_embed_match (logits is a plain output here, not scratch).
  */
 int b200_embed_match_wide(const void* A_bf16, const void* E_bf16, int64_t n_rows,
                           int n_cols, int dim, float score_thresh, float* probs,
