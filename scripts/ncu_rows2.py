@@ -22,6 +22,8 @@ else:
     seg_off = torch.from_numpy(np.concatenate([[0], np.cumsum(bench.RPN_LENS * B)]).astype(np.int32)).cuda()
     ki, kc = nms_batched(cb, cs, seg_off, 0.7, 1000, max(bench.RPN_LENS))
     rois, _, _ = select_topk(cb, cs, seg_off, ki, kc, B, 1000, 5000)
+if len(sys.argv) > 3 and sys.argv[3] == "bf16":
+    feats = [f.to(torch.bfloat16).contiguous(memory_format=torch.channels_last) for f in feats]
 mean = torch.empty((rois.shape[0], C), device="cuda")
 for v in [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "0").split(",")]:
     _ext.debug_set(False, True, v)

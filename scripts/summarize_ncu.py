@@ -27,7 +27,8 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
         "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
         "l1tex__m_l1tex2xbar_req_cycles_active.avg.pct_of_peak_sustained_elapsed",
-        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sectors_srcunit_tex_op_red.sum"]
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sectors_srcunit_tex_op_red.sum",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__cycles_elapsed.max"]
 
 
 def raw(rep):
@@ -70,7 +71,7 @@ def main():
                         if k in rec and rec[k] != "":
                             f.write("  %-90s %s %s\n" % (k, rec[k], units.get(k, "")))
                     f.write("\n")
-            if "roi_align_fwd_rows" in name and recs:
+            if name == "final_roi_align_fwd_rows.ncu-rep" and recs:
                 rec = recs[0]
                 conv = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}
                 rd = float(rec["dram__bytes_read.sum"]) * conv[units["dram__bytes_read.sum"]]
