@@ -58,6 +58,7 @@ SIGNATURES = {
     "b200_embed_match": (_i, [_vp, _vp, _i64, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200_linear_bf16": (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
     "b200_embed_match_wide": (_i, [_vp, _vp, _i64, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
+    "b200_mask_targets": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _f, _i, _vp, _vp]),
     "b200_paste_masks": (_i, [_vp, _vp, _i64, _i, _i, _i, _i, _f, _vp, _vp]),
     "b200_colmax_decode": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
     "b200_roi_pool_forward": (_i, [_vp, _i, _i, _i, _i, _vp, _i64, _f, _i, _i, _vp, _vp, _vp]),

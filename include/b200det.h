@@ -369,6 +369,21 @@ int b200_select_detections(const float* cand_boxes, const float* cand_scores,
                            int64_t* det_labels, int32_t* det_count, void* stream);
 
 /*
+ * Mask targets of the student straight from the pseudo-labels' mask_size x mask_size masks, without the
+ * full-image boolean masks in between: the composition of Masker's paste
+ * (modeling/roi_heads/mask_head/inference.py:96-186, as b200_paste_masks) with project_masks_on_boxes
+ * (modeling/roi_heads/mask_head/loss.py:11-42 = BinaryMaskList.crop at the proposal rounded half-to-even,
+ * bilinear resize to target_size x target_size with align_corners = False, `.type_as(bool)`).
+ *   masks [n_labels, mask_size, mask_size] fp32 probabilities; label_boxes [n_labels, 4] xyxy;
+ *   match [n_proposals] int32: the label each proposal was matched to (< 0: all-zero target);
+ *   proposals [n_proposals, 4] xyxy;  out [n_proposals, target_size, target_size] fp32 in {0, 1}.
+ */
+int b200_mask_targets(const float* masks, const float* label_boxes, const int32_t* match,
+                      const float* proposals, int64_t n_proposals, int mask_size, int padding,
+                      int im_h, int im_w, float thresh, int target_size, float* out,
+                      void* stream);
+
+/*
  * Mask paste: Masker.forward_single_image / paste_mask_in_image for all boxes of an
  * image in one launch (modeling/roi_heads/mask_head/inference.py:96-186): zero border of
  * `padding` pixels around each M x M mask probability map, the box grown by the same factor and

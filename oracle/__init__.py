@@ -315,6 +315,41 @@ def paste_masks(masks, boxes, im_h, im_w, thresh=0.5, padding=1):
     return out
 
 
+def mask_targets(masks, label_boxes, match, proposals, im_h, im_w, M, thresh=0.5, padding=1):
+    """project_masks_on_boxes (modeling/roi_heads/mask_head/loss.py:11-42) applied to the masks Masker pastes
+    (paste_masks above): per proposal, BinaryMaskList.crop of its matched label's full-image mask
+    (structures/segmentation_mask.py:118-137: Python round(), clamps), bilinear resize to M x M with
+    align_corners = False (:139-158) and `.type_as(bool)` (any non-zero blend is True).  -> fp32 [P, M, M]."""
+    f = np.float32
+    full = paste_masks(masks, label_boxes, im_h, im_w, thresh, padding)
+    proposals = _f32(proposals)
+    out = np.zeros((len(proposals), M, M), f)
+
+    def axis(n_in):
+        s = (f(n_in) / f(M)) * (np.arange(M, dtype=f) + f(0.5)) - f(0.5)
+        s = np.where(s < 0, f(0), s).astype(f)
+        i0 = np.minimum(np.floor(s).astype(np.int64), n_in - 1)
+        i1 = i0 + (i0 < n_in - 1)
+        l1 = np.clip(s - i0.astype(f), f(0), f(1)).astype(f)
+        return i0, i1, (f(1) - l1).astype(f), l1
+
+    for p, (box, k) in enumerate(zip(proposals, match)):
+        if k < 0:
+            continue
+        xmin, ymin, xmax, ymax = [round(float(b)) for b in box]
+        xmin = min(max(xmin, 0), im_w - 1)
+        ymin = min(max(ymin, 0), im_h - 1)
+        xmax = max(min(max(xmax, 0), im_w), xmin + 1)
+        ymax = max(min(max(ymax, 0), im_h), ymin + 1)
+        crop = full[k, ymin:ymax, xmin:xmax].astype(f)
+        yi0, yi1, yl0, yl1 = axis(crop.shape[0])
+        xi0, xi1, xl0, xl1 = axis(crop.shape[1])
+        top = xl0[None] * crop[yi0][:, xi0] + xl1[None] * crop[yi0][:, xi1]
+        bot = xl0[None] * crop[yi1][:, xi0] + xl1[None] * crop[yi1][:, xi1]
+        out[p] = ((yl0[:, None] * top + yl1[:, None] * bot) != 0).astype(f)
+    return out
+
+
 # --------------------------------------------------------------------------
 # Region -> class-embedding scoring (plain torch ops in the reference; numpy here)
 # --------------------------------------------------------------------------

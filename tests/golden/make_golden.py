@@ -202,6 +202,51 @@ def gen_masks(rng):
     return out
 
 
+def gen_mask_targets(rng):
+    """The student's mask targets through the reference's own code: Masker pastes the pseudo-labels' 14x14 masks
+    into full-image boolean masks (st_generalized_rcnn.py:267-272), SegmentationMask(mode='mask') wraps them, and
+    project_masks_on_boxes (mask_head/loss.py:11-42) crops / resizes them at the proposals.  pycocotools and cv2
+    are only imported by segmentation_mask.py, never called on this path: empty stub modules."""
+    for name in ("pycocotools", "pycocotools.mask", "cv2"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["pycocotools"].mask = sys.modules["pycocotools.mask"]
+    from maskrcnn_benchmark.modeling.roi_heads.mask_head.inference import Masker
+    from maskrcnn_benchmark.modeling.roi_heads.mask_head.loss import project_masks_on_boxes
+    from maskrcnn_benchmark.structures.bounding_box import BoxList
+    from maskrcnn_benchmark.structures.segmentation_mask import SegmentationMask
+    im_w, im_h, M = 333, 250, 14
+    label_boxes = np.array([[20.4, 30.6, 150.2, 200.9], [-12.0, -8.5, 80.0, 60.0], [200.0, 100.0, 340.0, 260.0],
+                            [100.2, 50.9, 101.6, 52.3], [5.0, 3.0, 330.0, 248.0]], np.float32)
+    k = len(label_boxes)
+    x = (rng.standard_normal((k, 1, 14, 14)) * 2).astype(np.float32)
+    x = (x + np.roll(x, 1, 2) + np.roll(x, 1, 3) + np.roll(x, (1, 1), (2, 3))) / 2
+    probs = torch.from_numpy(x).sigmoid()
+    labels_bl = BoxList(torch.from_numpy(label_boxes), (im_w, im_h), mode="xyxy")
+    full = Masker(threshold=0.5, padding=1)([probs], [labels_bl])[0]                 # [k, 1, H, W] bool
+    # proposals: jittered copies of the label boxes (positives), half-integer corners (round-half-to-even),
+    # boxes leaving the image, a sub-pixel one
+    match, props = [], []
+    for i in range(k):
+        for _ in range(6):
+            match.append(i)
+            props.append(label_boxes[i] + rng.normal(0, 6, 4).astype(np.float32))
+    props += [np.array([10.5, 20.5, 60.5, 90.5], np.float32), np.array([11.5, 21.5, 61.5, 91.5], np.float32),
+              np.array([-30.0, -20.0, 40.0, 50.0], np.float32), np.array([300.0, 200.0, 400.0, 300.0], np.float32),
+              np.array([120.2, 80.1, 120.4, 80.3], np.float32)]
+    match += [0, 0, 1, 2, 0]
+    props = np.stack(props).astype(np.float32)
+    props[:, 2] = np.maximum(props[:, 2], props[:, 0])
+    props[:, 3] = np.maximum(props[:, 3], props[:, 1])
+    match = np.array(match, np.int32)
+    seg = SegmentationMask(full[:, 0][torch.from_numpy(match).long()], (im_w, im_h), mode="mask")
+    want = project_masks_on_boxes(seg, BoxList(torch.from_numpy(props), (im_w, im_h), mode="xyxy"), M).numpy()
+    assert want.shape == (len(props), M, M) and set(np.unique(want)) <= {0.0, 1.0}
+    got = oracle.mask_targets(probs[:, 0].numpy(), label_boxes, match, props, im_h, im_w, M, 0.5, 1)
+    assert np.array_equal(got, want), "oracle.mask_targets != reference (%d pixels differ)" % int((got != want).sum())
+    return {"mt_probs": probs[:, 0].numpy(), "mt_label_boxes": label_boxes, "mt_match": match, "mt_proposals": props,
+            "mt_size": np.array([im_w, im_h, M]), "mt_targets_packed": np.packbits(want.astype(np.bool_).reshape(-1))}
+
+
 def main():
     install_reference()
     rng = np.random.default_rng(20221017)
@@ -211,6 +256,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "rpn.npz"), **gen_rpn(rng))
     np.savez_compressed(os.path.join(HERE, "box_head.npz"), **gen_box_head(rng))
     np.savez_compressed(os.path.join(HERE, "masks.npz"), **gen_masks(np.random.default_rng(99)))
+    np.savez_compressed(os.path.join(HERE, "mask_targets.npz"), **gen_mask_targets(np.random.default_rng(100)))
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KB")

@@ -149,3 +149,15 @@ def test_paste_masks_oracle_matches_reference_golden():
         assert (got != want).mean() <= 1e-5
         assert got[-1 if i == 0 else 0].any() == want[-1 if i == 0 else 0].any()
         o += n
+
+
+def test_mask_targets_oracle_equals_the_reference_golden():
+    """oracle.mask_targets against the output of the reference's own Masker + project_masks_on_boxes
+    (tests/golden/make_golden.py:gen_mask_targets)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "mask_targets.npz"))
+    im_w, im_h, m = [int(v) for v in g["mt_size"]]
+    n = len(g["mt_proposals"])
+    want = np.unpackbits(g["mt_targets_packed"])[: n * m * m].reshape(n, m, m).astype(np.float32)
+    got = oracle.mask_targets(g["mt_probs"], g["mt_label_boxes"], g["mt_match"], g["mt_proposals"], im_h, im_w, m)
+    assert np.array_equal(got, want) and 0.05 < want.mean() < 0.95

@@ -70,3 +70,43 @@ def test_masker_edge_cases():
         Masker(0.5, 1).forward_single_image(torch.zeros((1, 1, 14, 14)), BoxList(torch.zeros((1, 4)), (64, 48)))
     with pytest.raises(ValueError):
         Masker(-1.0, 1)
+
+
+def _boxlist(b, size):
+    from cvpr22_cross_modal_pseudo_labeling_b200.structures import BoxList
+    return BoxList(torch.from_numpy(np.asarray(b, np.float32)).cuda(), size, mode="xyxy")
+
+
+def test_mask_targets_equal_the_reference_golden():
+    """b200_mask_targets (paste o crop) == the reference's Masker + project_masks_on_boxes, 0 pixels off."""
+    import os
+    from cvpr22_cross_modal_pseudo_labeling_b200.modeling.roi_heads.mask_head.loss import project_masks_on_boxes
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "mask_targets.npz"))
+    im_w, im_h, m = [int(v) for v in g["mt_size"]]
+    n = len(g["mt_proposals"])
+    want = np.unpackbits(g["mt_targets_packed"])[: n * m * m].reshape(n, m, m).astype(np.float32)
+    got = project_masks_on_boxes(torch.from_numpy(g["mt_probs"]).cuda(), _boxlist(g["mt_label_boxes"], (im_w, im_h)),
+                                 torch.from_numpy(g["mt_match"]), _boxlist(g["mt_proposals"], (im_w, im_h)), m)
+    assert got.dtype == torch.float32 and got.is_cuda
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_mask_targets_random_boxes_vs_oracle_and_vs_paste_then_crop():
+    from cvpr22_cross_modal_pseudo_labeling_b200.modeling.roi_heads.mask_head.loss import project_masks_on_boxes
+    rng = np.random.default_rng(31)
+    im_w, im_h, k, p, m = 640, 427, 12, 300, 28
+    probs = 1 / (1 + np.exp(-(rng.standard_normal((k, 14, 14)) * 2))).astype(np.float32)
+    x1, y1 = rng.uniform(-20, im_w - 30, k), rng.uniform(-20, im_h - 30, k)
+    lb = np.stack([x1, y1, x1 + rng.uniform(2, 300, k), y1 + rng.uniform(2, 250, k)], 1).astype(np.float32)
+    match = rng.integers(-1, k, p).astype(np.int32)
+    props = (lb[np.maximum(match, 0)] + rng.normal(0, 10, (p, 4))).astype(np.float32)
+    props[:, 2:] = np.maximum(props[:, 2:], props[:, :2])
+    props[::7] = np.round(props[::7]) + 0.5                    # half-integer corners: round-half-to-even
+    want = oracle.mask_targets(probs, lb, match, props, im_h, im_w, m)
+    got = project_masks_on_boxes(torch.from_numpy(probs).cuda(), _boxlist(lb, (im_w, im_h)), torch.from_numpy(match),
+                                 _boxlist(props, (im_w, im_h)), m).cpu().numpy()
+    # the kernel's interpolated mask value may sit within rounding of the threshold where numpy's does not
+    assert (got != want).mean() <= 1e-4
+    assert np.all(got[match < 0] == 0)
+    assert project_masks_on_boxes(torch.zeros((0, 14, 14)).cuda(), _boxlist(np.zeros((0, 4)), (im_w, im_h)), torch.zeros((0,)),
+                                  _boxlist(np.zeros((0, 4)), (im_w, im_h)), m).numel() == 0
