@@ -328,6 +328,30 @@ def f_touched_bytes(rois, levels, shapes, scales, channels):
     return total
 
 
+_ORIG_AFFINITY = None
+
+
+def bind_to_gpu_numa_node(index):
+    """Run this process on the CPUs NVML names as local to GPU `index` BEFORE the pinned host buffers are
+    allocated (first touch decides the NUMA node of pinned pages): with 8 ranks each copying 1.47 GB per step the
+    e2e number is a host-memory / PCIe-uplink number, and remote pages make it worse.  Returns a short note."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [i for i in range(ncpu) if (words[i // 64] >> (i % 64)) & 1]
+        if cpus:
+            global _ORIG_AFFINITY
+            _ORIG_AFFINITY = os.sched_getaffinity(0)
+            os.sched_setaffinity(0, cpus)
+            return "cpus %d-%d (NVML affinity of GPU %d)" % (cpus[0], cpus[-1], index)
+    except Exception as e:
+        return "not bound (%s)" % type(e).__name__
+    return "not bound"
+
+
 # the library kernels one step launches (own kernels only; torch glue such as index_select / cat is not counted)
 STEP_KERNELS = ["nms_fused_kernel", "select_topk_kernel", "roi_order_kernel", "roi_align_fwd_rows",
                 "tc_gemm_kernel<linear> (fc stand-in)", "tc_gemm_kernel<linear> (emb_pred)", "tc_gemm_kernel<softmax>",
@@ -520,6 +544,7 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=dev)
     _ext.lib()
     _ext.debug_set(False, True, 0)
+    numa = bind_to_gpu_numa_node(local)
 
     # every rank draws its own synthetic batch unless --same-seed (then the max over ranks carries no
     # data-dependent spread: what is left of the N = 1 -> N step is the machine, not the boxes)
@@ -859,7 +884,8 @@ def run_gpu(args):
                                  if args.math == "fast" else None),
             "sustained": sustained,
             "clocks": clocks,
-            "e2e": {"value": rois_per_step / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+            "e2e": {"value": rois_per_step / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "host_numa": numa,
+                    "bound": "PCIe: %.2f GB of fp32 features cross the host link per step and GPU (the device part is %.2f ms)" % (h2d_bytes / 1e9, ms_step),
                     "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(rec_h.numel() * 4 + cnt_h.numel() * 4) // world},
             "gpu_launches": args.steps * len(STEP_KERNELS),
             "step_kernels": STEP_KERNELS,
@@ -875,6 +901,8 @@ def run_gpu(args):
         dist.destroy_process_group()
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
+            if _ORIG_AFFINITY is not None:   # the reference arm gets every host core back
+                os.sched_setaffinity(0, _ORIG_AFFINITY)
             try:
                 out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2",
                                       "--warmup", "1"], capture_output=True, text=True, timeout=600)
