@@ -46,6 +46,7 @@ SIGNATURES = {
     "b200_roi_align_forward_ws": (_i, [ctypes.POINTER(b200_level), _i, _i, _i, _i, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, ctypes.c_size_t, _vp]),
     "b200_roi_align_forward_bf16": (_i, [ctypes.POINTER(b200_level), _i, _i, _i, _i, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, ctypes.c_size_t, _vp]),
     "b200_roi_align_backward": (_i, [ctypes.POINTER(b200_level), _i, _i, _i, _i, _vp, _i64, _i, _i, _i, _vp, _vp]),
+    "b200_roi_align_backward_ws": (_i, [ctypes.POINTER(b200_level), _i, _i, _i, _i, _vp, _i64, _i, _i, _i, _vp, _vp, ctypes.c_size_t, _vp]),
     "b200_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "b200_nhwc_to_nchw": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "b200_nms_workspace_bytes": (_sz, [_i64, _i64, _i64]),

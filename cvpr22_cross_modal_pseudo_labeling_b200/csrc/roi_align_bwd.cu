@@ -134,8 +134,8 @@ __device__ __forceinline__ void red_col(char* const (&rp)[4], const bool (&use)[
 
 template <int kThreads, int kMinBlocks>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
-roi_align_bwd_march(const LevelGradTable lt, int C, const float* __restrict__ rois, int PH, int PW,
-                    int chunks_per_cta, const float* __restrict__ grad_out) {
+roi_align_bwd_march(const LevelGradTable lt, int C, const float* __restrict__ rois, const int32_t* __restrict__ order,
+                    int PH, int PW, int chunks_per_cta, const float* __restrict__ grad_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int NB = PH * PW;
   const bool swz = (NB & 3) == 0;
@@ -147,7 +147,8 @@ roi_align_bwd_march(const LevelGradTable lt, int C, const float* __restrict__ ro
 
   const int tid = threadIdx.x;
   const int groups = C / (kChunkB * chunks_per_cta);
-  const long long r = blockIdx.x / groups;
+  // `order` (optional): consecutive CTAs take RoIs that are neighbours in one feature map
+  const long long r = order ? (long long)order[blockIdx.x / groups] : (long long)(blockIdx.x / groups);
   const int c0 = (blockIdx.x % groups) * chunks_per_cta * kChunkB;
   const float* p = rois + r * 5;
   const int batch = (int)p[0];
@@ -242,6 +243,14 @@ extern "C" void b200_debug_bwd(int force_generic) { b200::g_bwd_force_generic = 
 extern "C" int b200_roi_align_backward(const b200_level_grad* levels, int n_levels, int layout, int batch,
                                        int channels, const float* rois, int64_t n_rois, int pooled_h,
                                        int pooled_w, int sampling_ratio, const float* grad_out, void* stream) {
+  return b200_roi_align_backward_ws(levels, n_levels, layout, batch, channels, rois, n_rois, pooled_h, pooled_w,
+                                    sampling_ratio, grad_out, nullptr, 0, stream);
+}
+
+extern "C" int b200_roi_align_backward_ws(const b200_level_grad* levels, int n_levels, int layout, int batch,
+                                          int channels, const float* rois, int64_t n_rois, int pooled_h,
+                                          int pooled_w, int sampling_ratio, const float* grad_out, void* workspace,
+                                          size_t workspace_bytes, void* stream) {
   using namespace b200;
   B200_REQUIRE(layout == B200_LAYOUT_NCHW || layout == B200_LAYOUT_NHWC, "roi_align_bwd: bad layout %d", layout);
   B200_REQUIRE(batch > 0 && channels > 0 && pooled_h > 0 && pooled_w > 0 && n_rois >= 0 && sampling_ratio >= 0,
@@ -275,18 +284,36 @@ extern "C" int b200_roi_align_backward(const b200_level_grad* levels, int n_leve
     B200_REQUIRE(grid < (int64_t)1 << 31, "roi_align_bwd: too many RoIs for one launch");
     const size_t smem = sizeof(float) * (kChunkB * NB + kTilePadFloats) + kMaxAxisSamples * sizeof(AxisEntry) +
                         (kMaxAxisSamples + 1) * sizeof(XSample) + kMaxCols * sizeof(int);
+    // visiting order (caller's scratch): the same (image, level, Morton cell) order as the forward
+    int32_t* order = nullptr;
+    if (workspace && workspace_bytes >= rows_order_workspace_bytes(n_rois) && (reinterpret_cast<uintptr_t>(workspace) & 3u) == 0 &&
+        n_rois > 1) {
+      LevelTable flt;
+      for (int l = 0; l < n_levels; ++l) {
+        flt.data[l] = lt.data[l];
+        flt.H[l] = lt.H[l];
+        flt.W[l] = lt.W[l];
+        flt.scale[l] = lt.scale[l];
+      }
+      flt.n_levels = lt.n_levels;
+      flt.k_min = lt.k_min;
+      flt.k_max = lt.k_max;
+      order = static_cast<int32_t*>(workspace);
+      int rc = launch_roi_order(flt, rois, n_rois, order, st);
+      if (rc != B200_OK) return rc;
+    }
     if (pooled_h <= 8) {
       auto kern = roi_align_bwd_march<128, 8>;
       static SmemHighWater hw;
       int rc = ensure_dynamic_smem(kern, smem, &hw, "roi_align_bwd: smem attribute");
       if (rc != B200_OK) return rc;
-      kern<<<(unsigned)grid, 128, smem, st>>>(lt, channels, rois, pooled_h, pooled_w, cpc, grad_out);
+      kern<<<(unsigned)grid, 128, smem, st>>>(lt, channels, rois, order, pooled_h, pooled_w, cpc, grad_out);
     } else {
       auto kern = roi_align_bwd_march<256, 4>;
       static SmemHighWater hw;
       int rc = ensure_dynamic_smem(kern, smem, &hw, "roi_align_bwd: smem attribute");
       if (rc != B200_OK) return rc;
-      kern<<<(unsigned)grid, 256, smem, st>>>(lt, channels, rois, pooled_h, pooled_w, cpc, grad_out);
+      kern<<<(unsigned)grid, 256, smem, st>>>(lt, channels, rois, order, pooled_h, pooled_w, cpc, grad_out);
     }
     B200_CHECK_LAUNCH("roi_align_bwd_march");
     return B200_OK;

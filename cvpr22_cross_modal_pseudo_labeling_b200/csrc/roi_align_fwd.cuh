@@ -92,5 +92,6 @@ bool rows_kernel_applies(const LevelTable& lt, int C, int PH, int PW);
 int launch_forward_rows(const LevelTable& lt, int C, bool bf16_maps, const float* rois, int64_t n_rois, float* out,
                         float* out_mean, int32_t* out_levels, int32_t* order_ws, int variant, cudaStream_t st);
 size_t rows_order_workspace_bytes(int64_t n_rois);
+int launch_roi_order(const LevelTable& lt, const float* rois, int64_t n_rois, int32_t* order, cudaStream_t st);
 
 }  // namespace b200

@@ -821,6 +821,16 @@ int launch_forward_rows(const LevelTable& lt, int C, bool bf16_maps, const float
   return B200_OK;
 }
 
+// the visiting order alone (also used by the backward: CTAs in this order scatter into neighbouring pixels,
+// so the reductions mostly meet lines that are still in the L2)
+int launch_roi_order(const LevelTable& lt, const float* rois, int64_t n_rois, int32_t* order, cudaStream_t st) {
+  B200_REQUIRE(n_rois < ((int64_t)1 << 31), "roi order: too many RoIs");
+  if (n_rois <= 0) return B200_OK;
+  roi_order_kernel<<<(unsigned)ceil_div<int64_t>(n_rois, kOrderChunk), kOrderThreads, 0, st>>>(lt, rois, (long long)n_rois, order);
+  B200_CHECK_LAUNCH("roi_order_kernel");
+  return B200_OK;
+}
+
 size_t rows_order_workspace_bytes(int64_t n_rois) { return n_rois > 0 ? sizeof(int32_t) * (size_t)n_rois : 0; }
 
 }  // namespace b200

@@ -170,10 +170,12 @@ def _backward(grad_out, rois, shapes, layouts_nhwc, scales, output_size, samplin
     r = rois.size(0)
     if r > 0:
         arr = _levels_array(grads, scales)
+        lib = _ext.lib()
+        ws = _workspace(lib.b200_roi_align_workspace_bytes(r), dev)   # the RoI visiting order of the marching kernel
         with torch.cuda.device(dev):
-            rc = _ext.lib().b200_roi_align_backward(
+            rc = lib.b200_roi_align_backward_ws(
                 arr, len(grads), _ext.B200_LAYOUT_NHWC if layouts_nhwc else _ext.B200_LAYOUT_NCHW, shapes[0][0],
-                shapes[0][1], _ext.ptr(rois), r, ph, pw, int(sampling_ratio), _ext.ptr(grad_out),
+                shapes[0][1], _ext.ptr(rois), r, ph, pw, int(sampling_ratio), _ext.ptr(grad_out), _ext.ptr(ws), ws.numel(),
                 _ext.stream_ptr(dev))
         _ext.check(rc, "b200_roi_align_backward")
     return grads

@@ -165,6 +165,18 @@ int b200_roi_align_backward(const b200_level_grad* levels, int n_levels,
                             const float* rois, int64_t n_rois, int pooled_h,
                             int pooled_w, int sampling_ratio,
                             const float* grad_out, void* stream);
+/*
+ * The same with caller-provided scratch (b200_roi_align_workspace_bytes(n_rois) bytes; NULL = the call above):
+ * the marching kernel then visits the RoIs in the forward's (image, level, Morton cell) order, so that the
+ * reductions of neighbouring RoIs meet lines that are still in the L2.  The gradient is a sum of atomic
+ * additions in either order (as in the reference, csrc/cuda/ROIAlign_cuda.cu:239-250).
+ */
+int b200_roi_align_backward_ws(const b200_level_grad* levels, int n_levels,
+                               int layout, int batch, int channels,
+                               const float* rois, int64_t n_rois, int pooled_h,
+                               int pooled_w, int sampling_ratio,
+                               const float* grad_out, void* workspace,
+                               size_t workspace_bytes, void* stream);
 
 /*
  * NCHW -> NHWC staging copy of one level ([B,C,H,W] contiguous -> [B,H,W,C]).
