@@ -135,6 +135,9 @@ def debug_set(force_generic=False, exact=True, variant=0):
                 the row-streaming kernel
       bit 5     (32) row-streaming kernel visits the RoIs in the order given (no ordering pass)
       bit 6     (64) row-streaming kernel without arithmetic (copy-pipeline probe; output is zeros)
+      bit 7     (128) two copy warps instead of four; bit 8 (256) output tile not stored
+      bit 9     (512) cycle counters of who waits for whom (read back with b200_debug_rows_stats)
+      bits 10-12 (1024 * k) ring entries per wait group (default: 1 for fp32 maps, 4 for bf16 maps)
     Process-wide; tests and probes reset it to (False, True, 0)."""
     lib().b200_debug_set(int(force_generic), int(exact), int(variant))
 

@@ -46,7 +46,7 @@ constexpr int kNS = 2 * kP;                      // samples per axis
 constexpr int kBins = kP * kP;                   // 49
 constexpr int kMaxList = 2 * kNS;                // distinct tap rows / columns of a RoI, at most
 constexpr int kRC = 256;                         // channels
-constexpr int kRingBytes = 168 * 1024;           // byte ring of tap rows
+constexpr int kRingBytes = 167 * 1024;           // byte ring of tap rows (with the tables: all of the 227 KB)
 // kPxB (template parameter below): bytes of one pixel, all channels -- 1024 for fp32 maps, 512 for bf16 maps
 // (bf16 in, fp32 arithmetic and output: the reference's amp.float_function semantics on bf16-rounded inputs,
 // layers/roi_align.py:57); the ring then holds twice as many pixels
@@ -62,8 +62,9 @@ constexpr int kTileFloats = kRC * kBins;
 // constants; a tap row feeding more than two output rows (bins narrower than ~1.3 pixels) is simply
 // listed -- and copied -- once per pair.
 // `place`: where the planner put the entry in the byte ring; `bar`: shared address of the entry's "full"
-// barrier, bit 31 = the phase parity to wait for (the planner knows the entry's sequence number, so the
-// consumers do no barrier arithmetic); RoiTab::dep: the copy may be issued once every ring entry with a
+// barrier, bit 31 = the phase parity to wait for (the planner tracks it, so the consumers do no barrier
+// arithmetic), bit 30 = the entry starts a WAIT GROUP: the copies of the group's entries all complete on this
+// barrier and the consumers wait for it before loading the entry's columns (other entries: no wait); RoiTab::dep: the copy may be issued once every ring entry with a
 // sequence number < dep has been given back (entries are given back in order)
 struct __align__(16) RingEntry {
   float w0, w1;
@@ -78,6 +79,8 @@ struct __align__(16) RoiTab {
   int gend[8];      // entries [gend[b-1], gend[b]) feed output rows b, b + 1
   RingEntry ent[kMaxList + 1];  // (+1: the consumers fetch headers one entry ahead)
   uint32_t dep[kMaxList];
+  int egrp[kMaxList];     // first entry of the group entry e belongs to (the group's "full" barrier is that entry's)
+                          // | entries in the group << 8
   int ent_y[kMaxList];    // feature row of entry e
   int run_pos[kMaxList], run_col[kMaxList], run_len[kMaxList];  // runs of consecutive tapped columns
 };
@@ -166,6 +169,12 @@ struct RoiPlace {
   int level, batch, H, W;
 };
 
+// (kProbe & 2): cycle counters of who waits for whom (b200_debug_rows_stats; scripts/probe_rows_stats.py)
+__device__ unsigned long long g_rows_stats[160][16];
+struct RowsStats {
+  long long full_wait = 0, tab_wait = 0, bar0 = 0, bar1 = 0, nent = 0, full_miss = 0;
+};
+
 // Producer warp: axis tables of RoI r.  Lanes 0-13 own the y samples, lanes 16-29 the x samples.
 // planner-private scratch (one copy; the tables above are what the other warps read)
 struct __align__(16) PlanScratch {
@@ -177,13 +186,14 @@ struct __align__(16) PlanScratch {
 struct __align__(16) RingState {
   uint32_t g0;    // ring entries of the RoIs placed so far
   uint32_t head;  // next free pixel of the ring
-  uint32_t pad[2];
+  uint32_t full_parity;  // bit i: the phase parity the next user of full_bar[i] waits for
+  uint32_t pad;
   uint32_t hist_place[kHist], hist_size[kHist];  // placement of the last kHist entries (pixels)
 };
 
 template <int kPxB>
 __device__ __forceinline__ RoiPlace build_rows_tab(const LevelTable& lt, const float* __restrict__ rois, long long r,
-                                                   RoiTab* tb, int lane, PlanScratch* sc) {
+                                                   RoiTab* tb, int lane, PlanScratch* sc, int gmax) {
   const RoiHeader h = load_roi(rois, r, lt);
   RoiPlace pl;
   pl.level = h.level;
@@ -332,6 +342,11 @@ __device__ __forceinline__ RoiPlace build_rows_tab(const LevelTable& lt, const f
         tb->ent_y[dst] = y;
         tb->ent[dst].w0 = sc->wy[lane][b];
         tb->ent[dst].w1 = b + 1 < kP ? sc->wy[lane][b + 1] : 0.f;
+        // wait groups: runs of at most gmax entries of the output-row group (gmax 1: every entry waits on a
+        // barrier of its own -- the round-1 scheme; larger: fewer waits, but the first entry of a run is only
+        // consumed when the whole run has landed)
+        const int j = dst - nent, j0 = j - j % gmax, cnt = min(gmax, __popc(bal) - j0);
+        tb->egrp[dst] = (nent + j0) | (cnt << 8);
       }
       nent += __popc(bal);
       if (lane == 0) tb->gend[b] = nent;
@@ -377,7 +392,7 @@ __device__ __forceinline__ void place_rows(RoiTab* tb, int lane, RingState* rs, 
   if (lane == 0) {
     tb->ent[nent].w0 = tb->ent[nent].w1 = 0.f;
     tb->ent[nent].place = 0u;
-    tb->ent[nent].bar = idle_a | 0x80000000u;
+    tb->ent[nent].bar = idle_a | 0xc0000000u;
   }
   if (nent == 0) return;
   const uint32_t s = (uint32_t)tb->ncols;  // >= 1
@@ -411,12 +426,22 @@ __device__ __forceinline__ void place_rows(RoiTab* tb, int lane, RingState* rs, 
       }
     }
     tb->ent[lane].place = place * (uint32_t)kPxB;
-    tb->ent[lane].bar = (full_a + 8u * (g % (uint32_t)kNBar)) | (((g / (uint32_t)kNBar) & 1u) << 31);
     tb->dep[lane] = dep;
   }
+  // "full" barriers: one per GROUP of entries (the entries feeding output rows b, b + 1), namely the barrier of the
+  // group's first entry -- the copies of the whole group complete on it and the consumers wait once per group.
+  // A barrier is therefore not used on every lap of the sequence numbers: its phase parity is tracked here.
+  const uint32_t bit = 1u << (g % (uint32_t)kNBar);
+  const bool first = lane < nent && (tb->egrp[lane] & 0xff) == lane;
+  const uint32_t par = rs->full_parity;
+  const uint32_t used = __reduce_or_sync(0xffffffffu, first ? bit : 0u);
+  if (lane < nent)
+    tb->ent[lane].bar = (full_a + 8u * (g % (uint32_t)kNBar)) | ((par & bit) ? 0x80000000u : 0u) | (first ? 0x40000000u : 0u);
+  __syncwarp();
   if (lane == nent - 1) {
     rs->head = place + s;
     rs->g0 = g0 + (uint32_t)nent;
+    rs->full_parity = par ^ used;
   }
 }
 
@@ -428,14 +453,34 @@ __device__ __forceinline__ void place_rows(RoiTab* tb, int lane, RingState* rs, 
 // small code, ~70 registers).
 template <int NK, int kProbe, int kPxB, typename Flush>
 __device__ __forceinline__ void consume_roi(uint32_t ent_a, uint32_t gend_a, uint32_t c0, uint32_t c1, uint32_t c2,
-                                            uint32_t c3, float4 wxv, uint32_t empty_off, int lane, Flush&& flush) {
+                                            uint32_t c3, float4 wxv, uint32_t empty_off, int lane, Flush&& flush, RowsStats& st) {
   float2 acc0[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, acc1[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
   float2 v[4][2];
 #pragma unroll
   for (int k = 0; k < 4; ++k) v[k][0] = v[k][1] = make_float2(0.f, 0.f);
-  auto load_cols = [&](uint32_t bar, uint32_t off) {
-    mbar_wait_a(bar & 0x7fffffffu, bar >> 31);
-    if (kProbe == 0) {
+  auto wait_group = [&](uint32_t bar) {
+    if ((kProbe & 2)) {
+      const long long t0 = clock64();
+      uint32_t ok;
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok)
+          : "r"(bar & 0x3fffffffu), "r"(bar >> 31)
+          : "memory");
+      if (!ok) {
+        ++st.full_miss;
+        mbar_wait_a(bar & 0x3fffffffu, bar >> 31);
+      }
+      st.full_wait += clock64() - t0;
+      ++st.nent;
+    } else {
+      mbar_wait_a(bar & 0x3fffffffu, bar >> 31);
+    }
+  };
+  auto load_cols = [&](uint32_t off) {
+    if (!(kProbe & 1)) {
       V4 t = lds_px<kPxB>(c0 + off);
       v[0][0] = t.lo, v[0][1] = t.hi;
       t = lds_px<kPxB>(c1 + off);
@@ -450,48 +495,55 @@ __device__ __forceinline__ void consume_roi(uint32_t ent_a, uint32_t gend_a, uin
       }
     }
   };
+  uint4 hdr;
+  // one entry: x pass over the columns held in v, give the entry back, fetch the next entry's columns (after the
+  // wait for its group when it starts one: kWait) while this one is accumulated into the two output rows
+  auto entry = [&](uint32_t ea) {
+    const uint4 nh = lds_u4(ea + 16u);
+    float2 u0 = make_float2(0.f, 0.f), u1 = make_float2(0.f, 0.f);
+    if (!(kProbe & 1)) {
+      const float2 wx0 = make_float2(wxv.x, wxv.x), wx1 = make_float2(wxv.y, wxv.y);
+      u0 = __fmul2_rn(wx0, v[0][0]);
+      u1 = __fmul2_rn(wx0, v[0][1]);
+      u0 = __ffma2_rn(wx1, v[1][0], u0);
+      u1 = __ffma2_rn(wx1, v[1][1], u1);
+      if (NK > 2) {
+        const float2 wx2 = make_float2(wxv.z, wxv.z);
+        u0 = __ffma2_rn(wx2, v[2][0], u0);
+        u1 = __ffma2_rn(wx2, v[2][1], u1);
+      }
+      if (NK > 3) {
+        const float2 wx3 = make_float2(wxv.w, wxv.w);
+        u0 = __ffma2_rn(wx3, v[3][0], u0);
+        u1 = __ffma2_rn(wx3, v[3][1], u1);
+      }
+    }
+    // this entry has been read: give it back, then fetch the next row while this one is accumulated
+    __syncwarp();
+    if (lane == 0) mbar_arrive_a((hdr.w & 0x3fffffffu) + empty_off);
+    if (nh.w & 0x40000000u) wait_group(nh.w);  // the next entry starts a wait group (or is the sentinel)
+    load_cols(nh.z);
+    const float w0 = __uint_as_float(hdr.x), w1 = __uint_as_float(hdr.y);
+    const float2 w0v = make_float2(w0, w0), w1v = make_float2(w1, w1);
+    acc0[0] = __ffma2_rn(w0v, u0, acc0[0]);
+    acc0[1] = __ffma2_rn(w0v, u1, acc0[1]);
+    acc1[0] = __ffma2_rn(w1v, u0, acc1[0]);
+    acc1[1] = __ffma2_rn(w1v, u1, acc1[1]);
+    hdr = nh;
+  };
   // (the entry after the last one is a sentinel whose barrier always passes: no "is there a next entry"
   // branch around the loads, so ptxas keeps the tap columns in place instead of copying them)
-  uint4 hdr = lds_u4(ent_a);
-  load_cols(hdr.w, hdr.z);
+  hdr = lds_u4(ent_a);
+  wait_group(hdr.w);
+  load_cols(hdr.z);
   uint32_t ea = ent_a;
 #pragma unroll 1
   for (int b = 0; b < kP; ++b) {
     const uint32_t end_a = ent_a + 16u * (uint32_t)lds_i32(gend_a + 4u * b);
+    // the copies of a wait group complete on ONE barrier (its first entry's), waited for before the group's
+    // first columns are loaded: inside a group the loop has no barrier in its dependency chain
 #pragma unroll 1
-    for (; ea < end_a; ea += 16u) {
-      const uint4 nh = lds_u4(ea + 16u);
-      float2 u0 = make_float2(0.f, 0.f), u1 = make_float2(0.f, 0.f);
-      if (kProbe == 0) {
-        const float2 wx0 = make_float2(wxv.x, wxv.x), wx1 = make_float2(wxv.y, wxv.y);
-        u0 = __fmul2_rn(wx0, v[0][0]);
-        u1 = __fmul2_rn(wx0, v[0][1]);
-        u0 = __ffma2_rn(wx1, v[1][0], u0);
-        u1 = __ffma2_rn(wx1, v[1][1], u1);
-        if (NK > 2) {
-          const float2 wx2 = make_float2(wxv.z, wxv.z);
-          u0 = __ffma2_rn(wx2, v[2][0], u0);
-          u1 = __ffma2_rn(wx2, v[2][1], u1);
-        }
-        if (NK > 3) {
-          const float2 wx3 = make_float2(wxv.w, wxv.w);
-          u0 = __ffma2_rn(wx3, v[3][0], u0);
-          u1 = __ffma2_rn(wx3, v[3][1], u1);
-        }
-      }
-      // this entry has been read: give it back, then fetch the next row while this one is accumulated
-      __syncwarp();
-      if (lane == 0) mbar_arrive_a((hdr.w & 0x7fffffffu) + empty_off);
-      // (a first poll of the next entry's barrier before this entry's arithmetic was measured slower)
-      load_cols(nh.w, nh.z);
-      const float w0 = __uint_as_float(hdr.x), w1 = __uint_as_float(hdr.y);
-      const float2 w0v = make_float2(w0, w0), w1v = make_float2(w1, w1);
-      acc0[0] = __ffma2_rn(w0v, u0, acc0[0]);
-      acc0[1] = __ffma2_rn(w0v, u1, acc0[1]);
-      acc1[0] = __ffma2_rn(w1v, u0, acc1[0]);
-      acc1[1] = __ffma2_rn(w1v, u1, acc1[1]);
-      hdr = nh;
-    }
+    for (; ea < end_a; ea += 16u) entry(ea);
     // (holding completed rows back for two groups, so that the first flush of a RoI never waits for the bulk
     // store of the previous one, was measured 2 % slower: registers and moves cost more than the wait)
     flush(b, acc0[0], acc0[1]);
@@ -503,12 +555,12 @@ __device__ __forceinline__ void consume_roi(uint32_t ent_a, uint32_t gend_a, uin
 
 // kCopyWarps: warps issuing the bulk copies (ring entry g belongs to warp g % kCopyWarps -- a single
 // warp's dependent instruction stream, ~40 instructions per entry, was what bounded the first version);
-// kProbe != 0: consumers skip the arithmetic (copy-engine throughput probe)
+// kProbe: 1 = consumers skip the arithmetic (copy-engine throughput probe), 2 = cycle counters (g_rows_stats)
 template <int kCopyWarps, int kProbe, int kPxB>
 __global__ void __launch_bounds__(32 * kConsWarps + 32 * kPlanWarps + 32 * kCopyWarps, 1)
 roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, const int32_t* __restrict__ order,
                    long long n_rois, float* __restrict__ out, float* __restrict__ out_mean,
-                   int32_t* __restrict__ out_levels, int flags) {
+                   int32_t* __restrict__ out_levels, int flags, int gmax) {
   // flags (probe, b200_debug_set variant bit 8): 1 = the output tile is not stored
   // (no integer round trip on this pointer: the compiler must keep seeing shared-space addresses,
   // or every access below turns into a generic LD.E / ST.E)
@@ -534,6 +586,7 @@ roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, const in
     mbar_init(&idle_bar, 1);
     ring_state.g0 = 0;
     ring_state.head = 0;
+    ring_state.full_parity = 0;
     for (int s = 0; s < kTabs; ++s) {
       mbar_init(&tab_full[s], 1);
       mbar_init(&tab_empty[s], kConsWarps + kCopyWarps);  // every reader of a table
@@ -552,25 +605,36 @@ roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, const in
     const int p = warp - kPlanWarp0;
     const uint32_t full_a = smem_u32(full_bar), idle_a = smem_u32(&idle_bar);
     int n = p, k = 0;
+    long long s_tab = 0, s_turn = 0;
+    const long long s_t0 = (kProbe & 2) ? clock64() : 0;
     for (long long i = blockIdx.x + (long long)p * gridDim.x; i < n_rois;
          i += (long long)kPlanWarps * gridDim.x, n += kPlanWarps, ++k) {
       const long long r = order ? (long long)order[i] : i;
       const int ti = n % kTabs;
+      long long t0 = (kProbe & 2) ? clock64() : 0;
       mbar_wait(&tab_empty[ti], (uint32_t)(((n / kTabs) & 1) ^ 1));  // (a fresh barrier passes)
-      const RoiPlace pl = build_rows_tab<kPxB>(lt, rois, r, tabs + ti, lane, &plan_scratch[p]);
+      if ((kProbe & 2)) s_tab += clock64() - t0;
+      const RoiPlace pl = build_rows_tab<kPxB>(lt, rois, r, tabs + ti, lane, &plan_scratch[p], gmax);
       if (lane == 0) {
         tabs[ti].roi = (int)r;
         if (out_levels) out_levels[r] = pl.level;
       }
       __syncwarp();
       // my turn: after planner p - 1 placed RoI n - 1 (planner 0's first turn is free)
+      t0 = (kProbe & 2) ? clock64() : 0;
       mbar_wait(&place_turn[p], (uint32_t)((k & 1) ^ (p == 0 ? 1 : 0)));
+      if ((kProbe & 2)) s_turn += clock64() - t0;
       place_rows<kPxB>(tabs + ti, lane, &ring_state, full_a, idle_a);
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&place_turn[(p + 1) % kPlanWarps]);
         mbar_arrive(&tab_full[ti]);
       }
+    }
+    if ((kProbe & 2) && p == 0 && lane == 0) {
+      g_rows_stats[blockIdx.x][10] = (unsigned long long)s_tab;
+      g_rows_stats[blockIdx.x][11] = (unsigned long long)s_turn;
+      g_rows_stats[blockIdx.x][12] = (unsigned long long)(clock64() - s_t0);
     }
     return;
   }
@@ -580,10 +644,14 @@ roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, const in
     const int cw = warp - kCopyWarp0;
     uint32_t g0 = 0;  // ring entries of the RoIs before this one
     int n = 0;
+    long long s_dep = 0, s_tab = 0, s_ndep = 0;
+    const long long s_t0 = (kProbe & 2) ? clock64() : 0;
     for (long long i = blockIdx.x; i < n_rois; i += gridDim.x, ++n) {
       const int ti = n % kTabs;
       const RoiTab* tb = tabs + ti;
+      long long t0 = (kProbe & 2) ? clock64() : 0;
       mbar_wait(&tab_full[ti], (uint32_t)((n / kTabs) & 1));
+      if ((kProbe & 2)) s_tab += clock64() - t0;
       const int nent = tb->nent, ncols = tb->ncols, nruns = tb->nruns;
       if (nent > 0) {
         const int level = tb->level, width = tb->width;
@@ -597,14 +665,27 @@ roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, const in
         }
 
         const uint32_t size = (uint32_t)ncols * kPxB;
+        // Entry g belongs to warp g % kCopyWarps, each warp taking its entries in order: a warp is then never a
+        // whole lap of the barriers ahead of the releases, which the parity waits below rely on.  The copies of
+        // a GROUP of entries complete on one "full" barrier -- its first entry's, armed by that entry's warp with
+        // the bytes of the whole group; a later entry of the group may complete before the barrier is armed
+        // (the transaction count is then transiently negative while the arrival is still pending).
         // first entry of this RoI that belongs to this warp
         int e = (int)((cw + kCopyWarps - g0 % kCopyWarps) % kCopyWarps);
         for (; e < nent; e += kCopyWarps) {
-          const uint32_t g = g0 + (uint32_t)e, bi = g % kNBar;
+          const int eg = tb->egrp[e], first = eg & 0xff;
+          const uint32_t bi = (g0 + (uint32_t)first) % kNBar;
           const uint32_t place = tb->ent[e].place, dep = tb->dep[e];
           // (dep - 1 >= g - kNBar, so the parity below names one phase unambiguously)
-          if (dep > 0) mbar_wait(&empty_bar[(dep - 1u) % kNBar], ((dep - 1u) / kNBar) & 1u);
-          if (lane == 0) mbar_arrive_expect_tx(&full_bar[bi], size);
+          if ((kProbe & 2)) {
+            t0 = clock64();
+            if (dep > 0 && !mbar_try_wait_a(smem_u32(&empty_bar[(dep - 1u) % kNBar]), ((dep - 1u) / kNBar) & 1u)) {
+              ++s_ndep;
+              mbar_wait(&empty_bar[(dep - 1u) % kNBar], ((dep - 1u) / kNBar) & 1u);
+            }
+            s_dep += clock64() - t0;
+          } else if (dep > 0) mbar_wait(&empty_bar[(dep - 1u) % kNBar], ((dep - 1u) / kNBar) & 1u);
+          if (lane == 0 && e == first) mbar_arrive_expect_tx(&full_bar[bi], size * (uint32_t)(eg >> 8));
           if (lane < nruns)
             bulk_g2s(ring + place + my_pos, gbase + (size_t)tb->ent_y[e] * width * kPxB, my_len, &full_bar[bi]);
         }
@@ -612,6 +693,12 @@ roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, const in
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&tab_empty[ti]);
+    }
+    if ((kProbe & 2) && cw == 0 && lane == 0) {
+      g_rows_stats[blockIdx.x][7] = (unsigned long long)s_dep;
+      g_rows_stats[blockIdx.x][8] = (unsigned long long)s_tab;
+      g_rows_stats[blockIdx.x][9] = (unsigned long long)(clock64() - s_t0);
+      g_rows_stats[blockIdx.x][13] = (unsigned long long)s_ndep;
     }
     return;
   }
@@ -640,10 +727,14 @@ roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, const in
   const uint64_t store_policy = policy_evict_first();
   // output row b of this thread's (4 channels, pw) is complete: into the tile.  Before the first row
   // of a RoI the bulk store of the previous RoI must have read the tile.
+  RowsStats st;
+  const long long s_t0 = (kProbe & 2) ? clock64() : 0;
   auto flush = [&](int b, float2 lo, float2 hi) {
     if (b == 0) {
+      const long long t0 = (kProbe & 2) ? clock64() : 0;
       if (tid == 0) bulk_wait_read();
       bar_consumers<kConsThreads>();
+      if ((kProbe & 2)) st.bar0 += clock64() - t0;
     }
     float a = lo.x, bb = lo.y, c = hi.x, d = hi.y;
     if (rot & 1) {
@@ -672,7 +763,9 @@ roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, const in
     const int ti = n % kTabs;
     const RoiTab* tb = tabs + ti;
     const uint32_t tb_a = tabs_a + (uint32_t)ti * (uint32_t)sizeof(RoiTab);
+    long long t0 = (kProbe & 2) ? clock64() : 0;
     mbar_wait(&tab_full[ti], (uint32_t)((n / kTabs) & 1));
+    if ((kProbe & 2)) st.tab_wait += clock64() - t0;
     const long long r = tb->roi;
     const int4 cxv = *reinterpret_cast<const int4*>(tb->cx[pw]);
     const float4 wxv = *reinterpret_cast<const float4*>(tb->wx[pw]);
@@ -680,9 +773,9 @@ roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, const in
     const uint32_t c0 = ring_a + cxv.x, c1 = ring_a + cxv.y, c2 = ring_a + cxv.z, c3 = ring_a + cxv.w;
     const uint32_t ent_a = tb_a + (uint32_t)offsetof(RoiTab, ent), gend_a = tb_a + (uint32_t)offsetof(RoiTab, gend);
     // (nk is the same for the whole warp: one specialised loop per RoI, no per-entry branches)
-    if (nk > 3) consume_roi<4, kProbe, kPxB>(ent_a, gend_a, c0, c1, c2, c3, wxv, empty_off, lane, flush);
-    else if (nk > 2) consume_roi<3, kProbe, kPxB>(ent_a, gend_a, c0, c1, c2, c3, wxv, empty_off, lane, flush);
-    else consume_roi<2, kProbe, kPxB>(ent_a, gend_a, c0, c1, c2, c3, wxv, empty_off, lane, flush);
+    if (nk > 3) consume_roi<4, kProbe, kPxB>(ent_a, gend_a, c0, c1, c2, c3, wxv, empty_off, lane, flush, st);
+    else if (nk > 2) consume_roi<3, kProbe, kPxB>(ent_a, gend_a, c0, c1, c2, c3, wxv, empty_off, lane, flush, st);
+    else consume_roi<2, kProbe, kPxB>(ent_a, gend_a, c0, c1, c2, c3, wxv, empty_off, lane, flush, st);
     // the tables of this RoI are no longer needed
     __syncwarp();
     if (lane == 0) mbar_arrive(&tab_empty[ti]);
@@ -690,7 +783,9 @@ roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, const in
     // ---- the [256 x 49] tile is complete: one contiguous 50 KB block of the NCHW output, a single
     // bulk store (TMA) that drains while the consumers are already in the next RoI's rows ----
     fence_proxy_async();  // this thread's tile writes -> visible to the async proxy
+    t0 = (kProbe & 2) ? clock64() : 0;
     bar_consumers<kConsThreads>();
+    if ((kProbe & 2)) st.bar1 += clock64() - t0;
     if (tid == 0 && !(flags & 1)) bulk_s2g(out + (size_t)r * kTileFloats, smem_u32(tile), kTileFloats * 4, store_policy);
     if (out_mean && tid < kRC) {
       const float* row = tile + tid * kBins;
@@ -701,6 +796,21 @@ roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, const in
     }
   }
   if (tid == 0) bulk_wait_all();  // the last store must have left shared memory before the CTA exits
+  if ((kProbe & 2) && lane == 0 && (warp == 0 || warp == kConsWarps - 1)) {
+    unsigned long long* o = g_rows_stats[blockIdx.x + (warp == 0 ? 0 : 0)];
+    if (warp == 0) {
+      o[0] = (unsigned long long)(clock64() - s_t0);
+      o[1] = (unsigned long long)st.full_wait;
+      o[2] = (unsigned long long)st.tab_wait;
+      o[3] = (unsigned long long)st.bar0;
+      o[4] = (unsigned long long)st.bar1;
+      o[5] = (unsigned long long)st.nent;
+      o[6] = (unsigned long long)st.full_miss;
+    } else {
+      o[14] = (unsigned long long)st.full_wait;
+      o[15] = (unsigned long long)(st.bar0 + st.bar1);
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -799,13 +909,26 @@ int launch_forward_rows(const LevelTable& lt, int C, bool bf16_maps, const float
     order = order_ws;
   }
   const int64_t grid = n_rois < sm_count() ? n_rois : sm_count();
+  // entries per wait group (build_rows_tab): measured best 1 for fp32 maps (the ring holds ~9 rows: waiting for
+  // several to land stalls the consumers), whole output-row groups for bf16 maps (twice the rows in flight);
+  // variant bits 10-12 override (tuning)
+  const int gmax = ((variant >> 10) & 7) ? ((variant >> 10) & 7) : (bf16_maps ? 4 : 1);
 #define B200_ROWS(CW, PROBE, PXB)                                                                               \
   do {                                                                                                          \
     static SmemHighWater hw;                                                                                    \
+    static int static_smem = -1;                                                                                \
+    if (static_smem < 0) {                                                                                      \
+      cudaFuncAttributes fa;                                                                                    \
+      int rc0 = check_cuda(cudaFuncGetAttributes(&fa, roi_align_fwd_rows<CW, PROBE, PXB>), "roi_align rows");   \
+      if (rc0 != B200_OK) return rc0;                                                                           \
+      static_smem = (int)fa.sharedSizeBytes;                                                                    \
+    }                                                                                                           \
+    B200_REQUIRE((size_t)static_smem + kRowsSmem <= (size_t)227 * 1024,                                         \
+                 "roi_align rows kernel: %d + %d bytes of shared memory", static_smem, (int)kRowsSmem);         \
     int rc = ensure_dynamic_smem(roi_align_fwd_rows<CW, PROBE, PXB>, kRowsSmem, &hw, "roi_align rows: smem");   \
     if (rc != B200_OK) return rc;                                                                               \
     roi_align_fwd_rows<CW, PROBE, PXB><<<(unsigned)grid, 32 * kConsWarps + 32 * kPlanWarps + 32 * CW, kRowsSmem, st>>>( \
-        lt, rois, order, (long long)n_rois, out, out_mean, out_levels, (variant >> 8) & 1);                     \
+        lt, rois, order, (long long)n_rois, out, out_mean, out_levels, (variant >> 8) & 1, gmax);               \
   } while (0)
   // (L2 prefetch of the planned rows -- bulk prefetches from the planner or one RoI ahead from a copy warp,
   // and LSU-side prefetch.global.L2 -- was measured 10-45 % SLOWER in all three forms: DESIGN.md)
@@ -814,6 +937,7 @@ int launch_forward_rows(const LevelTable& lt, int C, bool bf16_maps, const float
     if (variant & 128) B200_ROWS(2, 0, kRC * 2);
     else B200_ROWS(4, 0, kRC * 2);
   } else if (variant & 64) B200_ROWS(4, 1, kRC * 4);
+  else if (variant & 512) B200_ROWS(4, 2, kRC * 4);
   else if (variant & 128) B200_ROWS(2, 0, kRC * 4);
   else B200_ROWS(4, 0, kRC * 4);
 #undef B200_ROWS
@@ -829,6 +953,10 @@ int launch_roi_order(const LevelTable& lt, const float* rois, int64_t n_rois, in
   roi_order_kernel<<<(unsigned)ceil_div<int64_t>(n_rois, kOrderChunk), kOrderThreads, 0, st>>>(lt, rois, (long long)n_rois, order);
   B200_CHECK_LAUNCH("roi_order_kernel");
   return B200_OK;
+}
+
+extern "C" int b200_debug_rows_stats(unsigned long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, g_rows_stats, sizeof(g_rows_stats)) == cudaSuccess ? 0 : 1;
 }
 
 size_t rows_order_workspace_bytes(int64_t n_rois) { return n_rois > 0 ? sizeof(int32_t) * (size_t)n_rois : 0; }

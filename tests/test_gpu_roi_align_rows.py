@@ -119,6 +119,22 @@ def test_rows_kernel_visiting_order_does_not_change_results():
     assert np.array_equal(la[:300].cpu().numpy(), wl)
 
 
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("bf16", [False, True])
+def test_rows_kernel_wait_group_size_does_not_change_results(bf16):
+    """The copies of up to k consecutive ring entries may complete on one barrier (one consumer wait per group;
+    default 1 for fp32 maps, 4 for bf16 maps): scheduling only -- the results are bit-identical for every k."""
+    rng = np.random.default_rng(2607)
+    b, n = 2, 400
+    feats = _pyramid(rng, b, 256)
+    if bf16:
+        feats = [f.to(torch.bfloat16).contiguous(memory_format=torch.channels_last) for f in feats]
+    rois = torch.from_numpy(np.concatenate([synth.make_rois(rng, n, b, smin=6.0), EDGE]).astype(np.float32)).cuda()
+    outs = [_fwd(feats, synth.FPN_SCALES, rois, ROWS | (k << 10))[0] for k in (0, 1, 2, 3, 4, 7)]
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+
+
 @pytest.mark.timeout(180)
 def test_rows_kernel_full_size_against_exact():
     """BASELINE config #2 size (16 images x 1000 RoIs, 5.8 GB of taps): within 1e-5 of the
