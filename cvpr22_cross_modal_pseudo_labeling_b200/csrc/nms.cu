@@ -71,23 +71,49 @@ __device__ __forceinline__ uint32_t orderable_f(float f) {
 
 // Is box b (area_b, x centre / reach cb) suppressed by one of `count` kept boxes?  The three
 // lists sit in shared memory (32-bit addresses: float2 centre/reach, float4 box, float area).
-// Warp-uniform trip count; a kept box out of x reach of all 32 lanes costs one 64-bit load, three
-// float instructions and a vote, the IoU test runs only when some lane is near.
+// The 32 lanes of a warp hold boxes that sit side by side in the image (the chunk is handed out in
+// x order), so the warp first filters the list against the x interval of ITS alive boxes -- 32 kept
+// boxes per step, one per lane, merged with a ballot -- and only walks the survivors (a few per
+// cent of the list); for those a lane that is out of x reach (see x_reach) skips the IoU test.
+// Both filters are necessary conditions only (the warp interval is widened by a pixel against
+// fp32 rounding): verdicts are exactly those of testing every pair.
+// The thread's own box is only fetched (own_a: its shared address) when a kept box is near.
 __device__ __forceinline__ bool survives_list(uint32_t c_a, uint32_t b_a, uint32_t a_a, int count, bool alive,
-                                              const float4 b, float area_b, const float2 cb, float thresh) {
-  for (int r = 0; r < count; ++r, c_a += 8, b_a += 16, a_a += 4) {
-    float cx, cr;
-    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(cx), "=f"(cr) : "r"(c_a));
-    const bool near = alive && fabsf(cx - cb.x) - cr <= cb.y;
-    if (__any_sync(0xffffffffu, near)) {
-      if (near) {
-        float4 k;
-        float ak;
-        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(k.x), "=f"(k.y), "=f"(k.z), "=f"(k.w) : "r"(b_a));
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(ak) : "r"(a_a));
-        if (suppresses(k, ak, b, area_b, thresh)) alive = false;
+                                              uint32_t own_a, const float2 cb, float thresh, int lane) {
+  // [lo, hi]: union of the alive lanes' reach intervals (signed-orderable ints through redux)
+  const uint32_t olo = orderable_f(cb.x - cb.y) ^ 0x80000000u, ohi = orderable_f(cb.x + cb.y) ^ 0x80000000u;
+  // (a box with NaN coordinates is never near anything -- every comparison fails, as in nms_cpu -- and must
+  // not poison the window of its neighbours)
+  const bool win = alive && cb.x - cb.y <= cb.x + cb.y;
+  const int ilo = __reduce_min_sync(0xffffffffu, win ? (int)olo : 0x7fffffff);
+  const int ihi = __reduce_max_sync(0xffffffffu, win ? (int)ohi : (int)0x80000000);
+  if (ilo == 0x7fffffff) return alive;  // nobody alive (uniform)
+  const uint32_t ulo = (uint32_t)ilo ^ 0x80000000u, uhi = (uint32_t)ihi ^ 0x80000000u;
+  const float lo = __uint_as_float((ulo & 0x80000000u) ? (ulo & 0x7fffffffu) : ~ulo) - 1.0f;
+  const float hi = __uint_as_float((uhi & 0x80000000u) ? (uhi & 0x7fffffffu) : ~uhi) + 1.0f;
+  for (int r0 = 0; r0 < count; r0 += 32) {
+    const int k = r0 + lane;
+    float kx = 0.f, kr = -1.0e30f;  // (beyond the list: an empty interval)
+    if (k < count) asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(kx), "=f"(kr) : "r"(c_a + 8u * (uint32_t)k));
+    unsigned rel = __ballot_sync(0xffffffffu, kx + kr >= lo && kx - kr <= hi);
+    while (rel) {
+      const int r = r0 + __ffs(rel) - 1;
+      rel &= rel - 1;
+      float cx, cr;
+      asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(cx), "=f"(cr) : "r"(c_a + 8u * (uint32_t)r));
+      const bool near = alive && fabsf(cx - cb.x) - cr <= cb.y;
+      if (__any_sync(0xffffffffu, near)) {
+        if (near) {
+          float4 kk, b;
+          float ak;
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(kk.x), "=f"(kk.y), "=f"(kk.z), "=f"(kk.w) : "r"(b_a + 16u * (uint32_t)r));
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(ak) : "r"(a_a + 4u * (uint32_t)r));
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(own_a));
+          if (suppresses(kk, ak, b, legacy_area(b), thresh)) alive = false;
+        }
       }
     }
+    if (!__any_sync(0xffffffffu, alive)) break;
   }
   return alive;
 }
@@ -299,6 +325,21 @@ nms_sweep_kernel(const u64* __restrict__ mask, const int32_t* __restrict__ order
 constexpr int kFusedMaxSeg = 12288;  // 16 B * n of dynamic shared memory + kept list next to ~8 KB static
 constexpr int kChunkBoxes = 1024;    // lazy-update granularity of the early-stopping sweep
 
+// phase timers of the fused kernel (build with -DB200_NMS_STATS; scripts/probe_nms_step.py): cycles of thread 0
+#ifdef B200_NMS_STATS
+__device__ long long g_nms_stats[256][16];
+#define NMS_T(slot)                                 \
+  do {                                              \
+    if (tid == 0) {                                 \
+      const long long t_now = clock64();            \
+      g_nms_stats[blockIdx.x][slot] += t_now - t_last; \
+      t_last = t_now;                               \
+    }                                               \
+  } while (0)
+#else
+#define NMS_T(slot) do {} while (0)
+#endif
+
 template <int kThreads>
 __global__ void __launch_bounds__(kThreads, 1)
 nms_fused_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores,
@@ -327,6 +368,11 @@ nms_fused_kernel(const float4* __restrict__ boxes, const float* __restrict__ sco
     return;
   }
   const int nb = (n + kTile - 1) / kTile;
+#ifdef B200_NMS_STATS
+  long long t_last = clock64();
+  if (tid < 16) g_nms_stats[blockIdx.x][tid] = 0;
+  __syncthreads();
+#endif
 
   // ---- visiting order -------------------------------------------------------------------
   if (tid == 0) {
@@ -370,6 +416,7 @@ nms_fused_kernel(const float4* __restrict__ boxes, const float* __restrict__ sco
   }
   const bool can_stop = max_keep > 0 && !unsorted;
   __syncthreads();
+  NMS_T(0);  // load / order
 
   constexpr int G = kThreads / kTile;  // threads cooperating on one diagonal row
   constexpr int CPT = kTile / G;       // columns per thread
@@ -386,7 +433,17 @@ nms_fused_kernel(const float4* __restrict__ boxes, const float* __restrict__ sco
   // instead of the 25 of the IoU test.  Verdicts go to the "removed" bits with atomicOr.
   u64* pkeys = reinterpret_cast<u64*>(kla + kl_capacity + (kl_capacity & 1));
   int* perm = reinterpret_cast<int*>(pkeys + kChunkBoxes);
-  const int chunk_boxes = can_stop ? kChunkBoxes : nb * kTile;
+  constexpr int kPer = (kChunkBoxes + kThreads - 1) / kThreads;  // chunk boxes per thread
+  // per-thread state of the chunk's boxes this thread owns (early-stopping mode): position, alive, x centre / reach
+  int own_p[kPer];
+  bool own_alive[kPer];
+  float2 own_c[kPer];
+#pragma unroll
+  for (int k = 0; k < kPer; ++k) {
+    own_p[k] = 0;
+    own_alive[k] = false;
+    own_c[k] = make_float2(0.f, 0.f);
+  }
   int nk = 0;  // boxes in kl (uniform)
   bool done = false;
   int diag_tile = -1;  // tile whose diagonal words sit in diag[diag_tile & 1] (uniform)
@@ -411,15 +468,24 @@ nms_fused_kernel(const float4* __restrict__ boxes, const float* __restrict__ sco
     for (int d = G / 2; d > 0; d >>= 1) bits |= __shfl_xor_sync(0xffffffffu, bits, d);
     if (cg == 0) dbuf[r] = bits;
   };
-  for (int c0 = 0; c0 < n && !done; c0 += chunk_boxes) {
-    const int c1 = min(n, c0 + chunk_boxes);
+  for (int c0 = 0, c1 = 0; c0 < n && !done; c0 = c1) {
+    // chunk length: everything when the sweep cannot stop early; else up to kChunkBoxes, but only about as many
+    // boxes as the sweep can still need (1.5 x the boxes still to be kept + a tile): the work of a chunk --
+    // the pass against the kept list and step (c) -- grows with its length, and boxes behind the stopping
+    // point are wasted (s_nkept is uniform here: read between barriers)
+    int chunk_boxes = nb * kTile;
+    if (can_stop) {
+      const long long rem = max_keep - (long long)s_nkept;
+      const long long want = (rem + rem / 2 + 2 * kTile - 1) / kTile * kTile;
+      chunk_boxes = (int)(want < (long long)kChunkBoxes ? (want > 2 * kTile ? want : 2 * kTile) : kChunkBoxes);
+    }
+    c1 = min(n, c0 + chunk_boxes);
     if (can_stop) {
       // this chunk's boxes in x-centre order: a counting sort into 256 x buckets between the chunk's
       // smallest and largest centre (histogram with shared atomics, one scan, one scatter: 4 barriers; the
       // bitonic sort of the 1024 keys it replaces took 55).  The order inside a bucket is whatever the
       // atomics give -- it only decides which lane tests which box, never a verdict.
       const int clen = c1 - c0;
-      constexpr int kPer = (kChunkBoxes + kThreads - 1) / kThreads;
       int* bcnt = reinterpret_cast<int*>(pkeys);  // 256 counters, then their exclusive scan (pkeys is free here)
       int* brange = bcnt + 256;                    // orderable(min cx), orderable(max cx)
       if (tid < 256) bcnt[tid] = 0;
@@ -494,20 +560,26 @@ nms_fused_kernel(const float4* __restrict__ boxes, const float* __restrict__ sco
       for (int k = 0; k < kPer; ++k)
         if (bkt[k] >= 0) perm[bcnt[bkt[k]] + slot[k]] = tid + k * kThreads;
       __syncthreads();
+      NMS_T(1);  // chunk x order
+      // the boxes this thread owns for the whole chunk (x order: the lanes of a warp are neighbours in the image)
+#pragma unroll
+      for (int k = 0; k < kPer; ++k) {
+        const int pl = perm[tid + k * kThreads];
+        own_p[k] = c0 + (pl >= 0 ? pl : 0);
+        own_alive[k] = pl >= 0 && !((remv[own_p[k] >> 5] >> (own_p[k] & 31)) & 1u);
+        own_c[k] = x_reach(sb[own_p[k]], thresh);
+      }
       if (c0 > 0 && nk > 0) {
         // chunk vs everything kept so far
-        for (int t = tid; t < kChunkBoxes; t += kThreads) {
-          const int pl = perm[t];
-          const int p = c0 + (pl >= 0 ? pl : 0);
-          const bool alive0 = pl >= 0 && !((remv[p >> 5] >> (p & 31)) & 1u);
-          bool alive = alive0;
-          const float4 b = sb[p];
-          const float area_b = legacy_area(b);
-          const float2 cb = x_reach(b, thresh);
-          alive = survives_list(b200::smem_u32(klc), b200::smem_u32(kl), b200::smem_u32(kla), nk, alive, b, area_b, cb, thresh);
-          if (alive0 && !alive) atomicOr(&remv[p >> 5], 1u << (p & 31));
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+          const bool alive = survives_list(b200::smem_u32(klc), b200::smem_u32(kl), b200::smem_u32(kla), nk, own_alive[k],
+                                           b200::smem_u32(sb + own_p[k]), own_c[k], thresh, lane);
+          if (own_alive[k] && !alive) atomicOr(&remv[own_p[k] >> 5], 1u << (own_p[k] & 31));
+          own_alive[k] = alive;
         }
         __syncthreads();
+        NMS_T(2);  // chunk vs kept list
       }
     } else if (c0 > 0 && nk > 0) {
       // chunk vs everything kept so far
@@ -539,30 +611,42 @@ nms_fused_kernel(const float4* __restrict__ boxes, const float* __restrict__ sco
         diag_item(base, nrows, gone0, tid, diag[i & 1]);
         __syncthreads();
       }
+      NMS_T(3);  // diagonal words not precomputed
       // (b) in-tile chain on thread 0; meanwhile warps >= 1 compute the diagonal words of tile
       // i+1 (pure pairwise facts: rows that turn out to be removed are simply not used)
       const int nbase = base + kTile;
       const bool pre = nbase < n;  // uniform
-      if (tid == 0) {
+      if (tid < 32) {
+        // The greedy chain "row r is kept iff it is alive and no kept row before it suppresses it" is the unique
+        // fixed point of K -> alive & ~OR{d[j] : j in K} (d[j] only has bits above j, so bit r of the image
+        // depends on bits below r only: after t rounds the lowest t bits are final).  Warp 0 iterates it with
+        // two rows per lane and a 64-bit OR reduction per round; with few suppressions inside a tile it
+        // settles in 2-4 rounds instead of 64 dependent steps of one thread.
         const u64* dg = diag[i & 1];
-        u64 gone = gone0, kept = 0;
-#pragma unroll 8
-        for (int r = 0; r < nrows; ++r) {
-          const u64 d = dg[r];
-          if (!((gone >> r) & 1ull)) {
-            kept |= 1ull << r;
-            gone |= d;
-          }
+        const u64 alive0 = ~gone0 & live_mask;
+        const u64 d0 = lane < nrows ? dg[lane] : 0ull, d1 = lane + 32 < nrows ? dg[lane + 32] : 0ull;
+        u64 kept = alive0;
+        for (int round = 0; round < kTile; ++round) {
+          const u64 mine = (((kept >> lane) & 1ull) ? d0 : 0ull) | (((kept >> (lane + 32)) & 1ull) ? d1 : 0ull);
+          const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)mine);
+          const uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(mine >> 32));
+          const u64 next = alive0 & ~(((u64)hi << 32) | lo);
+          if (next == kept) break;
+          kept = next;
         }
-        s_kept = kept;
-        s_nkept += __popcll(kept);
-      } else if (pre && tid >= 32) {
+        if (tid == 0) {
+          s_kept = kept;
+          s_nkept += __popcll(kept);
+        }
+      } else if (pre) {
         const int nrows2 = min(kTile, n - nbase);
         for (int item = tid - 32; item < kThreads; item += kThreads - 32)
           diag_item(nbase, nrows2, 0ull, item, diag[(i + 1) & 1]);
       }
       if (pre) diag_tile = i + 1;
+      NMS_T(4);  // chain (thread 0)
       __syncthreads();
+      NMS_T(5);  // ... waiting for the next tile's diagonal words
       const u64 kept = s_kept;
       const int m = __popcll(kept);
       if (tid < kTile && ((kept >> tid) & 1ull)) {
@@ -577,27 +661,32 @@ nms_fused_kernel(const float4* __restrict__ boxes, const float* __restrict__ sco
           kla[nk + pos] = ab;
           klc[nk + pos] = x_reach(b, thresh);
         }
-        const int o = unsorted ? order[off + base + tid] : base + tid;
-        atomicOr(&keepbits[o >> 6], 1ull << (o & 63));
+        // (original positions; a 64-bit shared atomicOr is a CAS loop -- 64 threads on one word took 5.8 k cycles
+        // per tile -- so sorted input stores the tile's word directly and unsorted input uses 32-bit atomics)
+        if (unsorted) {
+          const int o = order[off + base + tid];
+          atomicOr(reinterpret_cast<uint32_t*>(keepbits) + (o >> 5), 1u << (o & 31));
+        }
       }
+      if (!unsorted && tid == 0) keepbits[i] = kept;
       nk += m;
       if (can_stop && (long long)s_nkept >= max_keep) {  // uniform: shared value
         done = true;
         break;
       }
       __syncthreads();
+      NMS_T(6);  // kept list update
       // (c) later boxes of this chunk vs this tile's kept boxes
       if (can_stop) {
-        for (int t = tid; t < kChunkBoxes; t += kThreads) {
-          const int pl = perm[t];
-          const int p = c0 + (pl >= 0 ? pl : 0);
-          const bool cand = pl >= 0 && p >= base + kTile && !((remv[p >> 5] >> (p & 31)) & 1u);
-          bool alive = cand;
-          const float4 b = sb[p];
-          const float area_b = legacy_area(b);
-          const float2 cb = x_reach(b, thresh);
-          alive = survives_list(b200::smem_u32(kbc), b200::smem_u32(kb), b200::smem_u32(ka), m, alive, b, area_b, cb, thresh);
-          if (cand && !alive) atomicOr(&remv[p >> 5], 1u << (p & 31));
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+          const bool cand = own_alive[k] && own_p[k] >= base + kTile;
+          const bool alive = survives_list(b200::smem_u32(kbc), b200::smem_u32(kb), b200::smem_u32(ka), m, cand,
+                                           b200::smem_u32(sb + own_p[k]), own_c[k], thresh, lane);
+          if (cand && !alive) {
+            atomicOr(&remv[own_p[k] >> 5], 1u << (own_p[k] & 31));
+            own_alive[k] = false;
+          }
         }
       } else
       for (int j0 = base + kTile + (tid & ~31); j0 < c1; j0 += kThreads) {
@@ -613,6 +702,10 @@ nms_fused_kernel(const float4* __restrict__ boxes, const float* __restrict__ sco
         if (lane == 0 && v) remv[j0 >> 5] = dead | v;
       }
       __syncthreads();
+      NMS_T(7);  // (c)
+#ifdef B200_NMS_STATS
+      if (tid == 0) g_nms_stats[blockIdx.x][9] += 1;
+#endif
     }
   }
   __syncthreads();
@@ -643,6 +736,7 @@ nms_fused_kernel(const float4* __restrict__ boxes, const float* __restrict__ sco
   }
   for (int p = limit + tid; p < n; p += kThreads) keep_idx[off + p] = -1;
   if (tid == 0) keep_cnt[s] = limit;
+  NMS_T(8);  // compaction
 }
 
 bool g_nms_force_bitmask = false;
@@ -818,6 +912,12 @@ select_topk_kernel(const float4* __restrict__ boxes, const float* __restrict__ s
   }
   if (tid == 0) count_out[img] = n_out;
 }
+
+#ifdef B200_NMS_STATS
+extern "C" int b200_debug_nms_stats(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, g_nms_stats, sizeof(g_nms_stats)) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 extern "C" void b200_debug_nms(int force_bitmask) { g_nms_force_bitmask = force_bitmask != 0; }
 
