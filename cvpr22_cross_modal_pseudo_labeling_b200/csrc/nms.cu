@@ -58,64 +58,18 @@ __device__ __forceinline__ bool suppresses(const float4 a, float area_a, const f
 // Necessary condition for suppresses(a, b): with ow the x-overlap, inter = ow * oh >= t * union
 // >= t * w * h of either box and oh <= h, so ow >= t * max(w_a, w_b); and ow <= (w_a + w_b) / 2 -
 // |cx_a - cx_b|.  Hence |cx_a - cx_b| <= (1 - t) / 2 * (w_a + w_b) = reach(a) + reach(b).
-// reach() is padded (1 % + 0.01 px) against fp32 rounding; thresh <= 0 disables the test.
-__device__ __forceinline__ float2 x_reach(const float4 b, float thresh) {
-  const float w = b.z - b.x + 1.0f;
-  const float r = thresh > 0.0f ? (1.0f - thresh) * 0.5f * w * 1.01f + 0.01f : 3.0e38f;
-  return make_float2(0.5f * (b.x + b.z), r);
+// reach() is padded (1 % + 0.01 px) against fp32 rounding; thresh <= 0 disables the test.  The same holds
+// in y with the heights.
+// the same necessary condition in both axes: (x centre, x reach, y centre, y reach)
+__device__ __forceinline__ float4 xy_reach(const float4 b, float thresh) {
+  const float w = b.z - b.x + 1.0f, h = b.w - b.y + 1.0f;
+  const float k = (1.0f - thresh) * 0.5f * 1.01f;
+  const bool on = thresh > 0.0f;
+  return make_float4(0.5f * (b.x + b.z), on ? k * w + 0.01f : 3.0e38f, 0.5f * (b.y + b.w), on ? k * h + 0.01f : 3.0e38f);
 }
 __device__ __forceinline__ uint32_t orderable_f(float f) {
   const uint32_t u = __float_as_uint(f);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-
-// Is box b (area_b, x centre / reach cb) suppressed by one of `count` kept boxes?  The three
-// lists sit in shared memory (32-bit addresses: float2 centre/reach, float4 box, float area).
-// The 32 lanes of a warp hold boxes that sit side by side in the image (the chunk is handed out in
-// x order), so the warp first filters the list against the x interval of ITS alive boxes -- 32 kept
-// boxes per step, one per lane, merged with a ballot -- and only walks the survivors (a few per
-// cent of the list); for those a lane that is out of x reach (see x_reach) skips the IoU test.
-// Both filters are necessary conditions only (the warp interval is widened by a pixel against
-// fp32 rounding): verdicts are exactly those of testing every pair.
-// The thread's own box is only fetched (own_a: its shared address) when a kept box is near.
-__device__ __forceinline__ bool survives_list(uint32_t c_a, uint32_t b_a, uint32_t a_a, int count, bool alive,
-                                              uint32_t own_a, const float2 cb, float thresh, int lane) {
-  // [lo, hi]: union of the alive lanes' reach intervals (signed-orderable ints through redux)
-  const uint32_t olo = orderable_f(cb.x - cb.y) ^ 0x80000000u, ohi = orderable_f(cb.x + cb.y) ^ 0x80000000u;
-  // (a box with NaN coordinates is never near anything -- every comparison fails, as in nms_cpu -- and must
-  // not poison the window of its neighbours)
-  const bool win = alive && cb.x - cb.y <= cb.x + cb.y;
-  const int ilo = __reduce_min_sync(0xffffffffu, win ? (int)olo : 0x7fffffff);
-  const int ihi = __reduce_max_sync(0xffffffffu, win ? (int)ohi : (int)0x80000000);
-  if (ilo == 0x7fffffff) return alive;  // nobody alive (uniform)
-  const uint32_t ulo = (uint32_t)ilo ^ 0x80000000u, uhi = (uint32_t)ihi ^ 0x80000000u;
-  const float lo = __uint_as_float((ulo & 0x80000000u) ? (ulo & 0x7fffffffu) : ~ulo) - 1.0f;
-  const float hi = __uint_as_float((uhi & 0x80000000u) ? (uhi & 0x7fffffffu) : ~uhi) + 1.0f;
-  for (int r0 = 0; r0 < count; r0 += 32) {
-    const int k = r0 + lane;
-    float kx = 0.f, kr = -1.0e30f;  // (beyond the list: an empty interval)
-    if (k < count) asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(kx), "=f"(kr) : "r"(c_a + 8u * (uint32_t)k));
-    unsigned rel = __ballot_sync(0xffffffffu, kx + kr >= lo && kx - kr <= hi);
-    while (rel) {
-      const int r = r0 + __ffs(rel) - 1;
-      rel &= rel - 1;
-      float cx, cr;
-      asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(cx), "=f"(cr) : "r"(c_a + 8u * (uint32_t)r));
-      const bool near = alive && fabsf(cx - cb.x) - cr <= cb.y;
-      if (__any_sync(0xffffffffu, near)) {
-        if (near) {
-          float4 kk, b;
-          float ak;
-          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(kk.x), "=f"(kk.y), "=f"(kk.z), "=f"(kk.w) : "r"(b_a + 16u * (uint32_t)r));
-          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(ak) : "r"(a_a + 4u * (uint32_t)r));
-          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(own_a));
-          if (suppresses(kk, ak, b, legacy_area(b), thresh)) alive = false;
-        }
-      }
-    }
-    if (!__any_sync(0xffffffffu, alive)) break;
-  }
-  return alive;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -314,16 +268,17 @@ nms_sweep_kernel(const u64* __restrict__ mask, const int32_t* __restrict__ order
 // ---------------------------------------------------------------------------------------
 // Fused single-kernel path (segments up to kFusedMaxSeg boxes): one CTA per segment keeps
 // the segment's boxes in shared memory and never materialises the N x N/64 bitmask.
-// Tiles of 64 boxes are visited in order; for tile i
-//   (a) the 64x64 diagonal IoU words are computed on the fly (rows already removed skip),
-//   (b) one thread resolves the in-tile chain,
-//   (c) every still-alive LATER box is tested only against the tile's KEPT boxes and the
-//       per-warp verdicts are merged with a ballot into the "removed" bit words.
-// Work is sum_i kept_i * alive_later_i pair tests instead of N^2/2, and stops as soon as
-// max_keep boxes are kept when the segment arrived sorted (RPN top-k output does).
+// Tiles of 64 boxes are visited in order.  Two sweeps:
+//   PUSH (no early stop, or unsorted input): for tile i (a) the 64x64 diagonal IoU words (rows
+//     already removed skip), (b) the in-tile chain on warp 0, (c) every still-alive LATER box is
+//     tested against the tile's KEPT boxes, warp verdicts merged with a ballot into the "removed"
+//     words.  Work is sum_i kept_i * alive_later_i pair tests instead of N^2/2.
+//   PULL (sorted input + max_keep: RPN top-k output): a tile is tested against the boxes kept so
+//     far -- held as a list sorted by x centre, of which a box only sees the window its x reach
+//     allows, with a y test before the IoU -- then chained and merged into the list; nothing behind
+//     the tile in which max_keep is reached is touched (details at the loop).
 // ---------------------------------------------------------------------------------------
-constexpr int kFusedMaxSeg = 12288;  // 16 B * n of dynamic shared memory + kept list next to ~8 KB static
-constexpr int kChunkBoxes = 1024;    // lazy-update granularity of the early-stopping sweep
+constexpr int kFusedMaxSeg = 12288;  // 16 B * n of dynamic shared memory + kept list next to ~9.5 KB static
 
 // phase timers of the fused kernel (build with -DB200_NMS_STATS; scripts/probe_nms_step.py): cycles of thread 0
 #ifdef B200_NMS_STATS
@@ -354,7 +309,6 @@ nms_fused_kernel(const float4* __restrict__ boxes, const float* __restrict__ sco
   __shared__ u64 diag[2][kTile];  // double-buffered: tile i+1's words are computed during tile i's chain
   __shared__ float4 kb[kTile];
   __shared__ float ka[kTile];
-  __shared__ float2 kbc[kTile];  // (x centre, x reach) of the tile's kept boxes
   __shared__ int scan[kMaxTiles];
   __shared__ u64 s_kept;
   __shared__ int s_nkept, s_unsorted;
@@ -418,37 +372,10 @@ nms_fused_kernel(const float4* __restrict__ boxes, const float* __restrict__ sco
   __syncthreads();
   NMS_T(0);  // load / order
 
-  constexpr int G = kThreads / kTile;  // threads cooperating on one diagonal row
+  constexpr int G = kThreads / kTile;  // threads cooperating on one row of a tile (consecutive lanes of one warp)
   constexpr int CPT = kTile / G;       // columns per thread
-  // When the sweep may stop early (sorted input + max_keep), later boxes are only brought up
-  // to date in chunks of kChunkBoxes: a chunk is first tested against the list of ALL boxes
-  // kept so far (kl), then swept tile by tile with step (c) confined to the chunk.  Boxes
-  // beyond the chunk in which max_keep is reached are never touched.
-  float4* kl = reinterpret_cast<float4*>(fused_smem + sizeof(float4) * (size_t)kl_offset_boxes);
-  float2* klc = reinterpret_cast<float2*>(kl + kl_capacity);  // (x centre, x reach) per kept box
-  float* kla = reinterpret_cast<float*>(klc + kl_capacity);
-  // In that mode the boxes of a chunk are handed to the threads in order of their x centre
-  // (perm): the 32 lanes of a warp then sit side by side in the image, and a kept box that is
-  // out of x reach of all of them (see x_reach) is rejected with 5 warp-uniform instructions
-  // instead of the 25 of the IoU test.  Verdicts go to the "removed" bits with atomicOr.
-  u64* pkeys = reinterpret_cast<u64*>(kla + kl_capacity + (kl_capacity & 1));
-  int* perm = reinterpret_cast<int*>(pkeys + kChunkBoxes);
-  constexpr int kPer = (kChunkBoxes + kThreads - 1) / kThreads;  // chunk boxes per thread
-  // per-thread state of the chunk's boxes this thread owns (early-stopping mode): position, alive, x centre / reach
-  int own_p[kPer];
-  bool own_alive[kPer];
-  float2 own_c[kPer];
-#pragma unroll
-  for (int k = 0; k < kPer; ++k) {
-    own_p[k] = 0;
-    own_alive[k] = false;
-    own_c[k] = make_float2(0.f, 0.f);
-  }
-  int nk = 0;  // boxes in kl (uniform)
-  bool done = false;
-  int diag_tile = -1;  // tile whose diagonal words sit in diag[diag_tile & 1] (uniform)
   // work item (row r, column group cg) of a tile's 64 x 64 diagonal block: CPT columns > r, the G
-  // lanes of a row OR their bits together (they are consecutive lanes of one warp)
+  // lanes of a row OR their bits together
   auto diag_item = [&](int tbase, int trows, u64 tgone, int item, u64* dbuf) {
     const int r = item / G, cg = item % G;
     u64 bits = 0;
@@ -468,137 +395,201 @@ nms_fused_kernel(const float4* __restrict__ boxes, const float* __restrict__ sco
     for (int d = G / 2; d > 0; d >>= 1) bits |= __shfl_xor_sync(0xffffffffu, bits, d);
     if (cg == 0) dbuf[r] = bits;
   };
-  for (int c0 = 0, c1 = 0; c0 < n && !done; c0 = c1) {
-    // chunk length: everything when the sweep cannot stop early; else up to kChunkBoxes, but only about as many
-    // boxes as the sweep can still need (1.5 x the boxes still to be kept + a tile): the work of a chunk --
-    // the pass against the kept list and step (c) -- grows with its length, and boxes behind the stopping
-    // point are wasted (s_nkept is uniform here: read between barriers)
-    int chunk_boxes = nb * kTile;
-    if (can_stop) {
-      const long long rem = max_keep - (long long)s_nkept;
-      const long long want = (rem + rem / 2 + 2 * kTile - 1) / kTile * kTile;
-      chunk_boxes = (int)(want < (long long)kChunkBoxes ? (want > 2 * kTile ? want : 2 * kTile) : kChunkBoxes);
+  // The greedy chain "row r is kept iff it is alive and no kept row before it suppresses it" is the unique
+  // fixed point of K -> alive & ~OR{d[j] : j in K} (d[j] only has bits above j, so bit r of the image
+  // depends on bits below r only: after t rounds the lowest t bits are final).  Warp 0 iterates it with
+  // two rows per lane and a 64-bit OR reduction per round; with few suppressions inside a tile it
+  // settles in 2-4 rounds instead of 64 dependent steps of one thread.
+  auto chain = [&](const u64* dg, int nrows, u64 alive0) -> u64 {
+    const u64 d0 = lane < nrows ? dg[lane] : 0ull, d1 = lane + 32 < nrows ? dg[lane + 32] : 0ull;
+    u64 kept = alive0;
+    for (int round = 0; round < kTile; ++round) {
+      const u64 mine = (((kept >> lane) & 1ull) ? d0 : 0ull) | (((kept >> (lane + 32)) & 1ull) ? d1 : 0ull);
+      const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)mine);
+      const uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(mine >> 32));
+      const u64 next = alive0 & ~(((u64)hi << 32) | lo);
+      if (next == kept) break;
+      kept = next;
     }
-    c1 = min(n, c0 + chunk_boxes);
-    if (can_stop) {
-      // this chunk's boxes in x-centre order: a counting sort into 256 x buckets between the chunk's
-      // smallest and largest centre (histogram with shared atomics, one scan, one scatter: 4 barriers; the
-      // bitonic sort of the 1024 keys it replaces took 55).  The order inside a bucket is whatever the
-      // atomics give -- it only decides which lane tests which box, never a verdict.
-      const int clen = c1 - c0;
-      int* bcnt = reinterpret_cast<int*>(pkeys);  // 256 counters, then their exclusive scan (pkeys is free here)
-      int* brange = bcnt + 256;                    // orderable(min cx), orderable(max cx)
-      if (tid < 256) bcnt[tid] = 0;
-      if (tid == 0) {
-        brange[0] = 0x7fffffff;
-        brange[1] = (int)0x80000000;
+    return kept;
+  };
+
+  if (can_stop) {
+    // ---- early-stopping sweep (sorted input + max_keep: the RPN case): PULL ----------------------------
+    // A box is kept iff no box kept BEFORE it suppresses it (nms_cpu.cpp:36-61 read from the side of the later
+    // box), so a tile only has to be tested against the boxes kept so far, and nothing behind the tile in which
+    // max_keep is reached is ever touched.  The kept boxes are held as a list of (x centre, position) SORTED BY
+    // x CENTRE: IoU >= t needs |cx_a - cx_b| <= reach_a + reach_b (xy_reach), so a box only looks at the window
+    // [cx - reach - rmax, cx + reach + rmax] of that list (two binary searches; rmax = largest reach kept so
+    // far) -- a few per cent of it -- with the G lanes of its row striding over the window.  Per tile:
+    //   A  pull (row r vs its window of the kept list) and the tile's 64 x 64 diagonal words, all threads;
+    //   B  warp 0: the in-tile chain from the rows that survived the pull;
+    //   C  the tile's newly kept boxes ranked among themselves by (x centre, position);
+    //   D  merge into the sorted list (every old entry moves up by the number of new entries before it).
+    // Boxes with NaN centre / reach never suppress anything (every comparison of nms_cpu fails) and are not
+    // listed.  Both filters are necessary conditions only (+1 px against fp32 rounding): the verdicts are
+    // those of testing every pair.
+    // list entry: (x centre, x reach, y centre, y reach) + the box's position, two buffers (the merge copies)
+    float4* xs_a = reinterpret_cast<float4*>(fused_smem + sizeof(float4) * (size_t)kl_offset_boxes);
+    float4* xs_b = xs_a + kl_capacity;
+    int* xp_a = reinterpret_cast<int*>(xs_b + kl_capacity);
+    int* xp_b = xp_a + kl_capacity;
+    __shared__ float4 rowc[kTile];  // (x centre, x reach, y centre, y reach) of the tile's rows
+    __shared__ int newk[kTile];     // the tile's listed kept rows, sorted by (x centre, row)
+    __shared__ uint32_t s_gone[2];
+    __shared__ u64 s_listed;
+    __shared__ float s_rmax;
+    if (tid == 0) {
+      s_gone[0] = s_gone[1] = 0u;
+      s_rmax = -3.0e38f;
+    }
+    __syncthreads();
+    const int r = tid / G, cg = tid % G;
+    const int row_lane0 = (lane / G) * G;  // first lane of this row's group
+    int nk = 0;                            // entries of the sorted list (uniform)
+    float4* xs = xs_a;                     // current list; the merge writes the other buffer
+    int* xp = xp_a;
+    for (int i = 0; i < nb; ++i) {
+      const int base = i * kTile;
+      const int nrows = min(kTile, n - base);
+      const u64 live_mask = nrows == 64 ? ~0ull : ((1ull << nrows) - 1);
+      // ---- A: pull + diagonal words ----
+      {
+        bool dead = false;
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 cb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < nrows) {
+          b = sb[base + r];
+          cb = xy_reach(b, thresh);
+          if (cg == 0) rowc[r] = cb;
+        }
+        if (nk > 0) {
+          const float R = cb.y + s_rmax + 1.0f;
+          int bound = 0;
+          if (r < nrows && cg < 2) {  // lane 0 of the row: first entry >= cx - R; lane 1: first entry > cx + R
+            const float key = cg == 0 ? cb.x - R : cb.x + R;
+            int lo = 0, hi = nk;
+            while (lo < hi) {
+              const int mid = (lo + hi) >> 1;
+              const float v = xs[mid].x;
+              if (cg == 0 ? (v < key) : (v <= key)) lo = mid + 1;
+              else hi = mid;
+            }
+            bound = lo;
+          }
+          const int jlo = __shfl_sync(0xffffffffu, bound, row_lane0), jhi = __shfl_sync(0xffffffffu, bound, row_lane0 + 1);
+          const float area_b = legacy_area(b);
+          for (int j = jlo + cg; j < jhi; j += G) {
+            const float4 kc = xs[j];
+            if (fabsf(kc.x - cb.x) - kc.y <= cb.y && fabsf(kc.z - cb.z) - kc.w <= cb.w) {  // near in x and in y
+              const float4 kbx = sb[xp[j]];
+              if (suppresses(kbx, legacy_area(kbx), b, area_b, thresh)) dead = true;
+            }
+          }
+#pragma unroll
+          for (int d = G / 2; d > 0; d >>= 1) dead |= __shfl_xor_sync(0xffffffffu, (int)dead, d) != 0;
+          if (cg == 0 && dead) atomicOr(&s_gone[r >> 5], 1u << (r & 31));
+        }
+        // (the diagonal words of tiles > 0 were computed by warps 1.. during the previous tile's chain)
+        if (i == 0) diag_item(base, nrows, 0ull, tid, diag[0]);
       }
       __syncthreads();
-      float cxs[kPer];
-      {
-        int mn = 0x7fffffff, mx = (int)0x80000000;
+      NMS_T(2);
+      // ---- B: chain, which of the kept rows are listed, largest reach ----
+      if (tid < 32) {
+        const u64 gone0 = ((u64)s_gone[1] << 32) | s_gone[0];
+        const u64 kept = chain(diag[i & 1], nrows, ~gone0 & live_mask);
+        const float4 c0v = rowc[lane], c1v = rowc[lane + 32];
+        const bool l0 = ((kept >> lane) & 1ull) && c0v.x == c0v.x && c0v.y == c0v.y;
+        const bool l1 = ((kept >> (lane + 32)) & 1ull) && c1v.x == c1v.x && c1v.y == c1v.y;
+        const u64 listed = ((u64)__ballot_sync(0xffffffffu, l1) << 32) | __ballot_sync(0xffffffffu, l0);
+        float rm = fmaxf(l0 ? c0v.y : -3.0e38f, l1 ? c1v.y : -3.0e38f);
 #pragma unroll
-        for (int k = 0; k < kPer; ++k) {
-          const int t = tid + k * kThreads;
-          cxs[k] = 0.f;
-          if (t < clen) {
-            const float4 b = sb[c0 + t];
-            cxs[k] = 0.5f * (b.x + b.z);
-            const int o = (int)(orderable_f(cxs[k]) ^ 0x80000000u);  // signed-orderable
-            mn = min(mn, o);
-            mx = max(mx, o);
+        for (int d = 16; d > 0; d >>= 1) rm = fmaxf(rm, __shfl_xor_sync(0xffffffffu, rm, d));
+        if (tid == 0) {
+          s_kept = kept;
+          s_listed = listed;
+          s_nkept += __popcll(kept);
+          s_rmax = fmaxf(s_rmax, rm);
+          s_gone[0] = s_gone[1] = 0u;
+          keepbits[i] = kept;  // (sorted input: positions are original indices)
+        }
+      } else if (base + kTile < n) {
+        // meanwhile: the diagonal words of the next tile (pure pairwise facts, all rows)
+        const int nbase = base + kTile, nrows2 = min(kTile, n - nbase);
+        for (int item = tid - 32; item < kThreads; item += kThreads - 32)
+          diag_item(nbase, nrows2, 0ull, item, diag[(i + 1) & 1]);
+      }
+      __syncthreads();
+      NMS_T(4);
+      if ((long long)s_nkept >= max_keep) break;  // uniform: shared value
+      // ---- C: rank of every listed row among the listed rows of this tile, by (x centre, row) ----
+      const u64 listed = s_listed;
+      const int mv = __popcll(listed);
+      {
+        int less = 0;
+        if (r < nrows && ((listed >> r) & 1ull)) {
+          const float cx = rowc[r].x;
+#pragma unroll
+          for (int k = 0; k < CPT; ++k) {
+            const int q = cg * CPT + k;
+            if (q < nrows && ((listed >> q) & 1ull)) {
+              const float cq = rowc[q].x;
+              less += (cq < cx || (cq == cx && q < r)) ? 1 : 0;
+            }
           }
         }
-        mn = __reduce_min_sync(0xffffffffu, mn);
-        mx = __reduce_max_sync(0xffffffffu, mx);
-        if (lane == 0) {
-          atomicMin(&brange[0], mn);
-          atomicMax(&brange[1], mx);
-        }
+#pragma unroll
+        for (int d = G / 2; d > 0; d >>= 1) less += __shfl_xor_sync(0xffffffffu, less, d);
+        if (cg == 0 && r < nrows && ((listed >> r) & 1ull)) newk[less] = r;
       }
       __syncthreads();
-      int bkt[kPer], slot[kPer];
+      NMS_T(6);
+      // ---- D: merge newk into the sorted list ----
       {
-        const uint32_t umn = (uint32_t)brange[0] ^ 0x80000000u, umx = (uint32_t)brange[1] ^ 0x80000000u;
-        const float lo = __uint_as_float((umn & 0x80000000u) ? (umn & 0x7fffffffu) : ~umn);
-        const float hi = __uint_as_float((umx & 0x80000000u) ? (umx & 0x7fffffffu) : ~umx);
-        const float scale = hi > lo ? 255.999f / (hi - lo) : 0.f;
-#pragma unroll
-        for (int k = 0; k < kPer; ++k) {
-          const int t = tid + k * kThreads;
-          bkt[k] = -1;
-          if (t < clen) {
-            bkt[k] = min(255, max(0, (int)((cxs[k] - lo) * scale)));
-            slot[k] = atomicAdd(&bcnt[bkt[k]], 1);
+        // (keys (x centre, position) are distinct; old positions are all below this tile's)
+        float4* xn = xs == xs_a ? xs_b : xs_a;
+        int* pn = xp == xp_a ? xp_b : xp_a;
+        for (int t = tid; t < nk + mv; t += kThreads) {
+          if (t < nk) {  // old entry: moves up by the number of new entries before it (x centre strictly smaller)
+            const float4 e = xs[t];
+            int lo = 0, hi = mv;
+            while (lo < hi) {
+              const int mid = (lo + hi) >> 1;
+              if (rowc[newk[mid]].x < e.x) lo = mid + 1;
+              else hi = mid;
+            }
+            xn[t + lo] = e;
+            pn[t + lo] = xp[t];
+          } else {  // new entry q: behind the q new entries before it and the old entries with centre <= its own
+            const int q = t - nk, row = newk[q];
+            const float4 e = rowc[row];
+            int lo = 0, hi = nk;
+            while (lo < hi) {
+              const int mid = (lo + hi) >> 1;
+              if (xs[mid].x <= e.x) lo = mid + 1;
+              else hi = mid;
+            }
+            xn[q + lo] = e;
+            pn[q + lo] = base + row;
           }
         }
+        xs = xn;
+        xp = pn;
+        nk += mv;
       }
       __syncthreads();
-      if (tid < 32) {  // exclusive scan of the 256 counters by one warp (8 per lane)
-        int c[8], run = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          c[j] = bcnt[8 * tid + j];
-          run += c[j];
-        }
-        int incl = run;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const int v = __shfl_up_sync(0xffffffffu, incl, d);
-          if (lane >= d) incl += v;
-        }
-        int ex = incl - run;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          bcnt[8 * tid + j] = ex;
-          ex += c[j];
-        }
-      }
-      for (int t = clen + tid; t < kChunkBoxes; t += kThreads) perm[t] = -1;  // padding
-      __syncthreads();
-#pragma unroll
-      for (int k = 0; k < kPer; ++k)
-        if (bkt[k] >= 0) perm[bcnt[bkt[k]] + slot[k]] = tid + k * kThreads;
-      __syncthreads();
-      NMS_T(1);  // chunk x order
-      // the boxes this thread owns for the whole chunk (x order: the lanes of a warp are neighbours in the image)
-#pragma unroll
-      for (int k = 0; k < kPer; ++k) {
-        const int pl = perm[tid + k * kThreads];
-        own_p[k] = c0 + (pl >= 0 ? pl : 0);
-        own_alive[k] = pl >= 0 && !((remv[own_p[k] >> 5] >> (own_p[k] & 31)) & 1u);
-        own_c[k] = x_reach(sb[own_p[k]], thresh);
-      }
-      if (c0 > 0 && nk > 0) {
-        // chunk vs everything kept so far
-#pragma unroll
-        for (int k = 0; k < kPer; ++k) {
-          const bool alive = survives_list(b200::smem_u32(klc), b200::smem_u32(kl), b200::smem_u32(kla), nk, own_alive[k],
-                                           b200::smem_u32(sb + own_p[k]), own_c[k], thresh, lane);
-          if (own_alive[k] && !alive) atomicOr(&remv[own_p[k] >> 5], 1u << (own_p[k] & 31));
-          own_alive[k] = alive;
-        }
-        __syncthreads();
-        NMS_T(2);  // chunk vs kept list
-      }
-    } else if (c0 > 0 && nk > 0) {
-      // chunk vs everything kept so far
-      for (int j0 = c0 + (tid & ~31); j0 < c1; j0 += kThreads) {
-        const int j = j0 + lane;
-        // warp-uniform trip count, predicated body: the lanes of a warp stay converged
-        // (a per-lane `break` made ptxas serialise the 32 lanes of this loop)
-        const uint32_t dead = remv[j0 >> 5];
-        bool alive = j < c1 && !((dead >> lane) & 1u);
-        const float4 b = sb[alive ? j : c0];
-        const float area_b = legacy_area(b);
-        for (int r = 0; r < nk; ++r)
-          if (alive && suppresses(kl[r], kla[r], b, area_b, thresh)) alive = false;
-        const uint32_t v = __ballot_sync(0xffffffffu, j < c1 && !((dead >> lane) & 1u) && !alive);
-        if (lane == 0 && v) remv[j0 >> 5] = dead | v;
-      }
-      __syncthreads();
+      NMS_T(7);
+#ifdef B200_NMS_STATS
+      if (tid == 0) g_nms_stats[blockIdx.x][9] += 1;
+#endif
     }
-    for (int i = c0 / kTile; i * kTile < c1; ++i) {
+  } else {
+    // ---- full sweep (no early stop, or unsorted input): PUSH ------------------------------------------------
+    // Tiles of 64 boxes in order: (a) diagonal words, (b) chain, (c) every still-alive LATER box is tested
+    // against the tile's KEPT boxes, warp verdicts merged by a ballot into the "removed" words.
+    int diag_tile = -1;  // tile whose diagonal words sit in diag[diag_tile & 1] (uniform)
+    for (int i = 0; i < nb; ++i) {
       const int base = i * kTile;
       const int nrows = min(kTile, n - base);
       const u64 gone0 = ((u64)remv[2 * i + 1] << 32) | remv[2 * i];
@@ -611,29 +602,12 @@ nms_fused_kernel(const float4* __restrict__ boxes, const float* __restrict__ sco
         diag_item(base, nrows, gone0, tid, diag[i & 1]);
         __syncthreads();
       }
-      NMS_T(3);  // diagonal words not precomputed
-      // (b) in-tile chain on thread 0; meanwhile warps >= 1 compute the diagonal words of tile
+      // (b) in-tile chain on warp 0; meanwhile the other warps compute the diagonal words of tile
       // i+1 (pure pairwise facts: rows that turn out to be removed are simply not used)
       const int nbase = base + kTile;
       const bool pre = nbase < n;  // uniform
       if (tid < 32) {
-        // The greedy chain "row r is kept iff it is alive and no kept row before it suppresses it" is the unique
-        // fixed point of K -> alive & ~OR{d[j] : j in K} (d[j] only has bits above j, so bit r of the image
-        // depends on bits below r only: after t rounds the lowest t bits are final).  Warp 0 iterates it with
-        // two rows per lane and a 64-bit OR reduction per round; with few suppressions inside a tile it
-        // settles in 2-4 rounds instead of 64 dependent steps of one thread.
-        const u64* dg = diag[i & 1];
-        const u64 alive0 = ~gone0 & live_mask;
-        const u64 d0 = lane < nrows ? dg[lane] : 0ull, d1 = lane + 32 < nrows ? dg[lane + 32] : 0ull;
-        u64 kept = alive0;
-        for (int round = 0; round < kTile; ++round) {
-          const u64 mine = (((kept >> lane) & 1ull) ? d0 : 0ull) | (((kept >> (lane + 32)) & 1ull) ? d1 : 0ull);
-          const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)mine);
-          const uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(mine >> 32));
-          const u64 next = alive0 & ~(((u64)hi << 32) | lo);
-          if (next == kept) break;
-          kept = next;
-        }
+        const u64 kept = chain(diag[i & 1], nrows, ~gone0 & live_mask);
         if (tid == 0) {
           s_kept = kept;
           s_nkept += __popcll(kept);
@@ -644,23 +618,14 @@ nms_fused_kernel(const float4* __restrict__ boxes, const float* __restrict__ sco
           diag_item(nbase, nrows2, 0ull, item, diag[(i + 1) & 1]);
       }
       if (pre) diag_tile = i + 1;
-      NMS_T(4);  // chain (thread 0)
       __syncthreads();
-      NMS_T(5);  // ... waiting for the next tile's diagonal words
       const u64 kept = s_kept;
       const int m = __popcll(kept);
       if (tid < kTile && ((kept >> tid) & 1ull)) {
         const int pos = __popcll(kept & ((1ull << tid) - 1));
         const float4 b = sb[base + tid];
-        const float ab = legacy_area(b);
         kb[pos] = b;
-        ka[pos] = ab;
-        kbc[pos] = x_reach(b, thresh);
-        if (can_stop && nk + pos < kl_capacity) {
-          kl[nk + pos] = b;
-          kla[nk + pos] = ab;
-          klc[nk + pos] = x_reach(b, thresh);
-        }
+        ka[pos] = legacy_area(b);
         // (original positions; a 64-bit shared atomicOr is a CAS loop -- 64 threads on one word took 5.8 k cycles
         // per tile -- so sorted input stores the tile's word directly and unsorted input uses 32-bit atomics)
         if (unsorted) {
@@ -669,59 +634,53 @@ nms_fused_kernel(const float4* __restrict__ boxes, const float* __restrict__ sco
         }
       }
       if (!unsorted && tid == 0) keepbits[i] = kept;
-      nk += m;
-      if (can_stop && (long long)s_nkept >= max_keep) {  // uniform: shared value
-        done = true;
-        break;
-      }
       __syncthreads();
-      NMS_T(6);  // kept list update
-      // (c) later boxes of this chunk vs this tile's kept boxes
-      if (can_stop) {
-#pragma unroll
-        for (int k = 0; k < kPer; ++k) {
-          const bool cand = own_alive[k] && own_p[k] >= base + kTile;
-          const bool alive = survives_list(b200::smem_u32(kbc), b200::smem_u32(kb), b200::smem_u32(ka), m, cand,
-                                           b200::smem_u32(sb + own_p[k]), own_c[k], thresh, lane);
-          if (cand && !alive) {
-            atomicOr(&remv[own_p[k] >> 5], 1u << (own_p[k] & 31));
-            own_alive[k] = false;
-          }
-        }
-      } else
-      for (int j0 = base + kTile + (tid & ~31); j0 < c1; j0 += kThreads) {
+      // (c) later boxes vs this tile's kept boxes
+      for (int j0 = base + kTile + (tid & ~31); j0 < n; j0 += kThreads) {
         const int j = j0 + lane;
+        // warp-uniform trip count, predicated body: the lanes of a warp stay converged
+        // (a per-lane `break` made ptxas serialise the 32 lanes of this loop)
         const uint32_t dead = remv[j0 >> 5];
-        const bool cand = j < c1 && !((dead >> lane) & 1u);
+        const bool cand = j < n && !((dead >> lane) & 1u);
         bool alive = cand;
         const float4 b = sb[cand ? j : base];
         const float area_b = legacy_area(b);
-        for (int r = 0; r < m; ++r)  // warp-uniform trip count, predicated body
-          if (alive && suppresses(kb[r], ka[r], b, area_b, thresh)) alive = false;
+        for (int rr = 0; rr < m; ++rr)
+          if (alive && suppresses(kb[rr], ka[rr], b, area_b, thresh)) alive = false;
         const uint32_t v = __ballot_sync(0xffffffffu, cand && !alive);
         if (lane == 0 && v) remv[j0 >> 5] = dead | v;
       }
       __syncthreads();
-      NMS_T(7);  // (c)
-#ifdef B200_NMS_STATS
-      if (tid == 0) g_nms_stats[blockIdx.x][9] += 1;
-#endif
     }
   }
   __syncthreads();
 
   // ---- ascending compaction of the kept original indices --------------------------------
-  for (int w = tid; w < kMaxTiles; w += kThreads) scan[w] = w < nb ? __popcll(keepbits[w]) : 0;
-  __syncthreads();
-  for (int d = 1; d < kMaxTiles; d <<= 1) {
-    int v[(kMaxTiles + kThreads - 1) / kThreads];
-    int k = 0;
-    for (int w = tid; w < kMaxTiles; w += kThreads) v[k++] = w >= d ? scan[w - d] : 0;
-    __syncthreads();
-    k = 0;
-    for (int w = tid; w < kMaxTiles; w += kThreads) scan[w] += v[k++];
-    __syncthreads();
+  // inclusive scan of the per-word counts by warp 0: kMaxTiles / 32 consecutive words per lane, one warp scan
+  if (tid < 32) {
+    constexpr int kW = kMaxTiles / 32;
+    static_assert(kMaxTiles % 32 == 0, "words per lane");
+    int c[kW], run = 0;
+#pragma unroll
+    for (int j = 0; j < kW; ++j) {
+      const int w = lane * kW + j;
+      c[j] = w < nb ? __popcll(keepbits[w]) : 0;
+      run += c[j];
+    }
+    int incl = run;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += v;
+    }
+    int acc = incl - run;
+#pragma unroll
+    for (int j = 0; j < kW; ++j) {
+      acc += c[j];
+      scan[lane * kW + j] = acc;
+    }
   }
+  __syncthreads();
   const int total = scan[kMaxTiles - 1];
   const int limit = (max_keep > 0 && max_keep < (long long)total) ? (int)max_keep : total;
   for (int w = tid; w < nb; w += kThreads) {
@@ -746,8 +705,7 @@ bool g_nms_force_bitmask = false;
 size_t fused_smem_bytes(size_t n_cap, size_t kl_cap) {
   size_t b = sizeof(float4) * n_cap;
   if (kl_cap > 0)
-    b += (sizeof(float4) + sizeof(float2) + sizeof(float)) * kl_cap + sizeof(float) * (kl_cap & 1) +
-         (sizeof(u64) + sizeof(int)) * (size_t)kChunkBoxes;
+    b += 2 * (sizeof(float4) + sizeof(int)) * kl_cap;  // two buffers of (centre / reach in x and y) + position
   return b;
 }
 
@@ -756,7 +714,7 @@ bool fused_applies(int64_t max_seg_len, int64_t max_keep) {
   if (g_nms_force_bitmask || max_seg_len > kFusedMaxSeg) return false;
   const size_t n_cap = (size_t)b200::ceil_div<int64_t>(max_seg_len, kTile) * kTile;
   const size_t kl_cap = max_keep > 0 ? (size_t)(max_keep < max_seg_len ? max_keep : max_seg_len) + kTile : 0;
-  return fused_smem_bytes(n_cap, kl_cap) + 9 * 1024 <= 227 * 1024;
+  return fused_smem_bytes(n_cap, kl_cap) + 10 * 1024 <= 227 * 1024;
 }
 
 struct Workspace {

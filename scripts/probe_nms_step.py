@@ -38,8 +38,7 @@ if hasattr(l, "b200_debug_nms_stats"):
     l.b200_debug_nms_stats.argtypes = [ctypes.c_void_p]
     assert l.b200_debug_nms_stats(buf) == 0
     a = np.frombuffer(buf, dtype=np.int64).reshape(256, 16)[:80].astype(np.float64)
-    names = ["load/order", "chunk x order", "chunk vs kept", "diag (not precomputed)", "chain", "wait next diag",
-             "kept update", "(c) tile kept vs chunk", "compaction", "tiles"]
+    names = ["load/order", "-", "A pull + diagonal words", "-", "B chain", "-", "C rank new", "D merge", "compaction", "tiles"]
     lens = np.repeat(np.asarray(bench.RPN_LENS), B) if len(bench.RPN_LENS) * B == 80 else np.tile(np.asarray(bench.RPN_LENS), B)
     seg_len = (seg_off[1:] - seg_off[:-1]).cpu().numpy()
     for L in sorted(set(seg_len.tolist()), reverse=True):
