@@ -151,6 +151,13 @@ def test_rows_kernel_full_size_against_exact():
     assert torch.equal(lv, le)
     err = (got - exact).abs()
     assert bool((err <= RTOL * exact.abs() + 1e-6).all()), float(err.max())
+    # ... and the bench's configuration touches the oracle directly: 200 random RoIs of the full-size batch
+    pick = np.sort(rng.choice(rois.shape[0], 200, replace=False))
+    want, wl = oracle.pooler_forward([f.cpu().contiguous().numpy() for f in feats], rois[pick].cpu().numpy(),
+                                     synth.FPN_SCALES, 7, 7, 2)
+    assert np.array_equal(lv[pick].cpu().numpy(), wl)
+    np.testing.assert_allclose(got[pick].cpu().numpy(), want, rtol=RTOL, atol=1e-6)
+    assert np.array_equal(exact[pick].cpu().numpy(), want)   # the exact kernel: bit-identical
     ones = [torch.full_like(f, 3.25) for f in feats]
     del feats
     inside = (rois[:, 1] >= 0) & (rois[:, 2] >= 0) & (rois[:, 3] <= synth.IMG_W - 1) & (rois[:, 4] <= synth.IMG_H - 1)
