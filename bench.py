@@ -436,13 +436,17 @@ def roofline_passes(torch, dev, feats, scales, shapes, state, cand_boxes, cand_s
         c4 = torch.randn((1, 1024, 50, 84), device=dev, generator=gen1)
         r1 = torch.from_numpy(synth.make_rois(np.random.default_rng(1235), 1000, 1)).to(dev)
         flush = torch.empty((256 << 20,), dtype=torch.uint8, device=dev)    # the 17 MB map would sit in the L2
-        for layout, x in (("NCHW (the reference's layout)", c4), ("channels_last", c4.contiguous(memory_format=torch.channels_last))):
+        from cvpr22_cross_modal_pseudo_labeling_b200.layers.roi_align import nhwc_cache
+        for layout, x in (("NCHW (the reference's layout; timed with the NHWC re-layout the Pooler stages)", c4),
+                          ("channels_last", c4.contiguous(memory_format=torch.channels_last))):
             ts = []
             for _ in range(5):
                 flush.zero_()
+                nhwc_cache.entries.clear()
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
-                _forward([x], (1.0 / 16,), r1, (14, 14), 0, math="exact")
+                # (what modeling.Pooler does with an NCHW-contiguous map: b200_nchw_to_nhwc, then roi_align_fwd_tile)
+                _forward([nhwc_cache.get(x) if x.is_contiguous() else x], (1.0 / 16,), r1, (14, 14), 0, math="exact")
                 b.record()
                 b.synchronize()
                 ts.append(a.elapsed_time(b))

@@ -154,6 +154,191 @@ roi_align_fwd_generic(const LevelTable lt, int C, const float* __restrict__ rois
 }
 
 // ---------------------------------------------------------------------------------------
+// Tiled gather (NHWC, ANY sampling ratio incl. the adaptive sampling_ratio 0, C % 64 == 0, a [64 x NB] tile that
+// fits in shared memory): the reference's shipped C4 pooler -- 1024 channels, 14 x 14 bins, sampling_ratio 0,
+// config/defaults.py:301-305 -- where the output (803 KB per RoI) is almost all of the traffic.
+// One CTA per (RoI, 64-channel chunk).  The sample geometry of both axes is evaluated once into two
+// shared-memory tables (the generic gather re-evaluates it per thread and tap); a thread = (channel quad, bin),
+// 16 quads side by side = 256 contiguous bytes of a pixel per tap; the arithmetic and its order are the generic
+// gather's (bit-identical to ROIAlign_cpu when kExact); results leave through the shared [64 x NB] tile as one
+// contiguous block of the NCHW output (128-bit streaming stores) -- the generic gather stores 4 bytes per lane at
+// a stride of 4 * NB floats, a sector per element.  A RoI whose sample count exceeds the tables takes the
+// generic path inside the same launch.
+// ---------------------------------------------------------------------------------------
+constexpr int kTileThreads = 256;
+constexpr int kTileMaxAx = 128;  // samples per axis held in the tables (PH * grid_h, PW * grid_w)
+
+struct __align__(16) TileTap {
+  int lo, hi;  // element offsets of the two taps: y * W * C (rows), x * C (columns)
+  float l, h;  // their weights; both 0: the sample is out of range and contributes nothing
+};
+
+// row of channel c in the [kCh x NB] tile: shifted by 4 floats per 8 channels when NB % 4 == 0 (as tile_row)
+template <int kCh>
+constexpr size_t tile_kernel_smem(int NB) {
+  return sizeof(float) * ((size_t)kCh * NB + kTilePadFloats) + 2 * kTileMaxAx * sizeof(TileTap);
+}
+
+// kCh: channels per CTA.  32 (a tile of 25 KB at 14 x 14: four CTAs leave ~130 KB of the SM's L1 for the taps --
+// with 64-channel tiles the shared-memory carve-out left ~30 KB and every tap went to the L2) or 64.
+template <bool kExact, int kCh>
+__global__ void __launch_bounds__(kTileThreads)
+roi_align_fwd_tile(const LevelTable lt, int C, const float* __restrict__ rois, int PH, int PW, int sampling_ratio,
+                   float* __restrict__ out, float* __restrict__ out_mean, int32_t* __restrict__ out_levels) {
+  extern __shared__ __align__(16) unsigned char tile_smem[];
+  constexpr int kQuads = kCh / 4, kSlots = kTileThreads / kQuads;
+  const int NB = PH * PW;
+  const bool swz = (NB & 3) == 0;
+  float* tile = reinterpret_cast<float*>(tile_smem);
+  TileTap* ytab = reinterpret_cast<TileTap*>(tile_smem + sizeof(float) * (kCh * NB + kTilePadFloats));
+  TileTap* xtab = ytab + kTileMaxAx;
+  const int n_cchunks = C / kCh;
+  const long long r = blockIdx.x / n_cchunks;
+  const int c_begin = (blockIdx.x % n_cchunks) * kCh;
+  const int tid = threadIdx.x;
+  const RoiHeader h = load_roi(rois, r, lt);
+  float* out_roi = out + (size_t)r * C * NB;
+  if (c_begin == 0 && tid == 0 && out_levels) out_levels[r] = h.level;
+  if (h.level < 0) {
+    zero_fill(out_roi + (size_t)c_begin * NB, kCh * NB, tid, kTileThreads);
+    if (out_mean) zero_fill(out_mean + (size_t)r * C + c_begin, kCh, tid, kTileThreads);
+    return;
+  }
+  const int H = lt.H[h.level], W = lt.W[h.level];
+  const RoiGeom g = roi_geometry(h.x1, h.y1, h.x2, h.y2, lt.scale[h.level], PH, PW, sampling_ratio);
+  if (PH * g.grid_h > kTileMaxAx || PW * g.grid_w > kTileMaxAx) {  // (a huge RoI on a fine map)
+    generic_roi<kExact, B200_LAYOUT_NHWC>(lt.data[h.level], C, H, W, h.batch, g, PH, PW, c_begin, kCh, out_roi, tid,
+                                          kTileThreads);
+    if (out_mean) {
+      __syncthreads();  // (this CTA's own global writes)
+      if (tid < kCh) {
+        const float* p = out_roi + (size_t)(c_begin + tid) * NB;
+        float s = 0.f;
+        for (int k = 0; k < NB; ++k) s = __fadd_rn(s, p[k]);
+        out_mean[(size_t)r * C + c_begin + tid] = __fdiv_rn(s, (float)NB);
+      }
+    }
+    return;
+  }
+  for (int i = tid; i < PH * g.grid_h + PW * g.grid_w; i += kTileThreads) {
+    const bool is_y = i < PH * g.grid_h;
+    const int j = is_y ? i : i - PH * g.grid_h;
+    const int grid = is_y ? g.grid_h : g.grid_w;
+    const int p = j / grid, k = j - p * grid;
+    bool ok;
+    const AxisTap t = is_y ? axis_sample(g.start_h, p, g.bin_h, k, grid, H, ok) : axis_sample(g.start_w, p, g.bin_w, k, grid, W, ok);
+    const int stride = is_y ? W * C : C;
+    TileTap e;
+    e.lo = ok ? t.lo * stride : 0;
+    e.hi = ok ? t.hi * stride : 0;
+    e.l = ok ? t.l : 0.f;
+    e.h = ok ? t.h : 0.f;
+    (is_y ? ytab : xtab)[j] = e;
+  }
+  __syncthreads();
+  const int q = tid % kQuads, slot = tid / kQuads;
+  const float* base = lt.data[h.level] + (size_t)h.batch * H * W * C + c_begin + 4 * q;
+  const int n_samples = g.grid_h * g.grid_w;
+  const float count = (float)n_samples;
+  // acc / count: a power-of-two count (1, 2, 4, 8, 16: nine RoIs in ten of the C4 pooler) is an exact scaling, so the
+  // product with 1 / count is the correctly rounded quotient as well; other counts take the IEEE division
+  const bool pow2 = (n_samples & (n_samples - 1)) == 0;
+  const float inv_count = __fdiv_rn(1.0f, count);
+  const int row0 = tile_row(4 * q, NB, swz), row1 = tile_row(4 * q + 1, NB, swz), row2 = tile_row(4 * q + 2, NB, swz),
+            row3 = tile_row(4 * q + 3, NB, swz);
+  // (ph, pw) of the thread's bins without a division per bin
+  const int step_ph = kSlots / PW, step_pw = kSlots - step_ph * PW;
+  int ph = slot / PW, pw = slot - ph * PW;
+  for (int bin = slot; bin < NB; bin += kSlots) {
+    const TileTap* yt = ytab + ph * g.grid_h;
+    const TileTap* xt = xtab + pw * g.grid_w;
+    // two fp32 lanes per issue slot where possible (FMUL2 / FADD2 / FFMA2 round each lane like the scalar instruction;
+    // the exact mode keeps the reference's order ((w1 v1 + w2 v2) + w3 v3) + w4 v4, every operation rounded separately)
+    float2 acc_lo = make_float2(0.f, 0.f), acc_hi = make_float2(0.f, 0.f);
+    for (int iy = 0; iy < g.grid_h; ++iy) {
+      const TileTap ty = yt[iy];
+      if (ty.h == 0.f && ty.l == 0.f) continue;  // (a valid sample has h = 1 - l > 0 or l > 0)
+      const float* rlo = base + ty.lo;
+      const float* rhi = base + ty.hi;
+      const float2 tyh = make_float2(ty.h, ty.h), tyl = make_float2(ty.l, ty.l);
+      for (int ix = 0; ix < g.grid_w; ++ix) {
+        const TileTap tx = xt[ix];
+        if (tx.h == 0.f && tx.l == 0.f) continue;
+        const float4 v1 = __ldg(reinterpret_cast<const float4*>(rlo + tx.lo));
+        const float4 v2 = __ldg(reinterpret_cast<const float4*>(rlo + tx.hi));
+        const float4 v3 = __ldg(reinterpret_cast<const float4*>(rhi + tx.lo));
+        const float4 v4 = __ldg(reinterpret_cast<const float4*>(rhi + tx.hi));
+        const float2 txhl = make_float2(tx.h, tx.l);
+        const float2 w12 = __fmul2_rn(tyh, txhl), w34 = __fmul2_rn(tyl, txhl);  // (w1, w2), (w3, w4)
+        const float2 w1 = make_float2(w12.x, w12.x), w2 = make_float2(w12.y, w12.y), w3 = make_float2(w34.x, w34.x),
+                     w4 = make_float2(w34.y, w34.y);
+        if (kExact) {
+          // products as FMUL2, the three sums as scalar FADDs: ptxas (12.9) contracts mul.rn.f32x2 + add.rn.f32x2 into
+          // FFMA2 although both carry an explicit rounding mode (it never does for the scalar forms), which would
+          // break the bit-exactness; the accumulation below has no product operand and stays a FADD2
+          const float2 p1l = __fmul2_rn(w1, make_float2(v1.x, v1.y)), p1h = __fmul2_rn(w1, make_float2(v1.z, v1.w));
+          const float2 p2l = __fmul2_rn(w2, make_float2(v2.x, v2.y)), p2h = __fmul2_rn(w2, make_float2(v2.z, v2.w));
+          const float2 p3l = __fmul2_rn(w3, make_float2(v3.x, v3.y)), p3h = __fmul2_rn(w3, make_float2(v3.z, v3.w));
+          const float2 p4l = __fmul2_rn(w4, make_float2(v4.x, v4.y)), p4h = __fmul2_rn(w4, make_float2(v4.z, v4.w));
+          float2 s_lo, s_hi;
+          s_lo.x = __fadd_rn(__fadd_rn(__fadd_rn(p1l.x, p2l.x), p3l.x), p4l.x);
+          s_lo.y = __fadd_rn(__fadd_rn(__fadd_rn(p1l.y, p2l.y), p3l.y), p4l.y);
+          s_hi.x = __fadd_rn(__fadd_rn(__fadd_rn(p1h.x, p2h.x), p3h.x), p4h.x);
+          s_hi.y = __fadd_rn(__fadd_rn(__fadd_rn(p1h.y, p2h.y), p3h.y), p4h.y);
+          acc_lo = __fadd2_rn(acc_lo, s_lo);
+          acc_hi = __fadd2_rn(acc_hi, s_hi);
+        } else {
+          acc_lo = __ffma2_rn(w1, make_float2(v1.x, v1.y), acc_lo);
+          acc_hi = __ffma2_rn(w1, make_float2(v1.z, v1.w), acc_hi);
+          acc_lo = __ffma2_rn(w2, make_float2(v2.x, v2.y), acc_lo);
+          acc_hi = __ffma2_rn(w2, make_float2(v2.z, v2.w), acc_hi);
+          acc_lo = __ffma2_rn(w3, make_float2(v3.x, v3.y), acc_lo);
+          acc_hi = __ffma2_rn(w3, make_float2(v3.z, v3.w), acc_hi);
+          acc_lo = __ffma2_rn(w4, make_float2(v4.x, v4.y), acc_lo);
+          acc_hi = __ffma2_rn(w4, make_float2(v4.z, v4.w), acc_hi);
+        }
+      }
+    }
+    if (pow2 || !kExact) {
+      const float2 ic = make_float2(inv_count, inv_count);
+      acc_lo = __fmul2_rn(acc_lo, ic);
+      acc_hi = __fmul2_rn(acc_hi, ic);
+    } else {
+      acc_lo = make_float2(__fdiv_rn(acc_lo.x, count), __fdiv_rn(acc_lo.y, count));
+      acc_hi = make_float2(__fdiv_rn(acc_hi.x, count), __fdiv_rn(acc_hi.y, count));
+    }
+    tile[row0 + bin] = acc_lo.x;
+    tile[row1 + bin] = acc_lo.y;
+    tile[row2 + bin] = acc_hi.x;
+    tile[row3 + bin] = acc_hi.y;
+    ph += step_ph;
+    pw += step_pw;
+    if (pw >= PW) {
+      pw -= PW;
+      ++ph;
+    }
+  }
+  __syncthreads();
+  // the [kCh x NB] block is contiguous in the NCHW output: 128-bit streaming stores
+  {
+    float4* dst = reinterpret_cast<float4*>(out_roi + (size_t)c_begin * NB);
+    const float4* src = reinterpret_cast<const float4*>(tile);
+    if (!swz) {
+      for (int i = tid; i < kCh * NB / 4; i += kTileThreads) __stcs(dst + i, src[i]);
+    } else {
+      const int rowv = NB >> 2;
+      for (int i = tid; i < kCh * rowv; i += kTileThreads) __stcs(dst + i, src[i + ((i / rowv) >> 3)]);
+    }
+  }
+  if (out_mean && tid < kCh) {
+    const float* row = tile + tile_row(tid, NB, swz);
+    float s = 0.f;
+    for (int i = 0; i < NB; ++i) s = __fadd_rn(s, row[i]);
+    out_mean[(size_t)r * C + c_begin + tid] = __fdiv_rn(s, (float)NB);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // Marching kernel (NHWC, sampling_ratio == 2, PH,PW <= 16, C % 64 == 0).
 // One CTA per (RoI, 64-channel chunk); shared memory holds only the two axis tables and
 // the [64 x NB] output tile, so many CTAs share an SM and the RoI's patch lives in L1.
@@ -340,6 +525,28 @@ int launch_forward(const LevelTable& lt, int layout, int C, const float* rois, i
       if (g_variant == 2) return launch_march<true, 256, 2, 4>(lt, C, rois, n_rois, PH, PW, out, out_mean, out_levels, st);
       return launch_march<true, 256, 3, 4>(lt, C, rois, n_rois, PH, PW, out, out_mean, out_levels, st);
     }
+  }
+  // NHWC, any sampling ratio: the tiled gather when the [32 x NB] tile fits (tuning: g_variant & 16384 = the plain
+  // gather, & 8192 = 64 channels per CTA)
+  if (!g_force_generic && !(g_variant & 16384) && layout == B200_LAYOUT_NHWC && C % kChunk == 0 && (NB * 32) % 4 == 0 &&
+      tile_kernel_smem<kChunk>(NB) <= (size_t)100 * 1024) {
+    if (g_variant & 8192) {
+      auto kern = roi_align_fwd_tile<kExact, 64>;
+      static SmemHighWater hw;
+      int rc = ensure_dynamic_smem(kern, tile_kernel_smem<64>(NB), &hw, "roi_align tile: smem attribute");
+      if (rc != B200_OK) return rc;
+      kern<<<(unsigned)(n_rois * (C / 64)), kTileThreads, tile_kernel_smem<64>(NB), st>>>(lt, C, rois, PH, PW, sr, out, out_mean,
+                                                                                       out_levels);
+    } else {
+      auto kern = roi_align_fwd_tile<kExact, 32>;
+      static SmemHighWater hw;
+      int rc = ensure_dynamic_smem(kern, tile_kernel_smem<32>(NB), &hw, "roi_align tile: smem attribute");
+      if (rc != B200_OK) return rc;
+      kern<<<(unsigned)(n_rois * (C / 32)), kTileThreads, tile_kernel_smem<32>(NB), st>>>(lt, C, rois, PH, PW, sr, out, out_mean,
+                                                                                       out_levels);
+    }
+    B200_CHECK_LAUNCH("roi_align_fwd_tile");
+    return B200_OK;
   }
   // generic: pick channels per CTA so that a CTA has >= ~2k units of work
   int c_per_cta = C;

@@ -216,9 +216,11 @@ nhwc_cache = _NhwcCache()
 
 
 def _stageable(f, sampling_ratio):
-    """NCHW-contiguous CUDA map that the marching kernels could take if it were NHWC."""
-    return (f.is_cuda and f.dtype == torch.float32 and f.dim() == 4 and sampling_ratio == 2 and f.size(1) % 64 == 0 and f.size(1) > 1 and
-            f.is_contiguous() and not f.is_contiguous(memory_format=torch.channels_last))
+    """NCHW-contiguous CUDA map that the NHWC kernels could take if it were NHWC: the marching / row-streaming
+    kernels at sampling_ratio 2, the tiled gather (roi_align_fwd_tile) at any other ratio -- e.g. the
+    reference's shipped C4 pooler, sampling_ratio 0 on a [1, 1024, H/16, W/16] map (config/defaults.py:301-305)."""
+    return (f.is_cuda and f.dtype == torch.float32 and f.dim() == 4 and sampling_ratio >= 0 and f.size(1) % 64 == 0 and
+            f.size(1) > 1 and f.is_contiguous() and not f.is_contiguous(memory_format=torch.channels_last))
 
 
 class _ROIAlignMulti(Function):

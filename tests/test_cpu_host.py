@@ -43,6 +43,23 @@ def test_library_is_sm100a_with_tcgen05_and_tma():
         assert mnemonic in out, mnemonic
 
 
+def test_exact_roi_align_kernels_contain_no_packed_fma():
+    """ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 although both carry a rounding mode (it never does
+    for the scalar forms), which silently breaks bit-exactness: the exact (<true, ...>) instantiations of the
+    RoIAlign forward kernels must not contain an FFMA2."""
+    from cvpr22_cross_modal_pseudo_labeling_b200 import _ext
+    if not os.path.exists("/usr/local/cuda/bin/cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-sass", _ext.LIB_PATH], capture_output=True, text=True).stdout
+    seen = 0
+    for block in out.split("Function : ")[1:]:
+        name = block.split("\n", 1)[0]
+        if ("roi_align_fwd_tileILb1" in name or "roi_align_fwd_marchILb1" in name or "roi_align_fwd_genericILb1" in name):
+            seen += 1
+            assert "FFMA2" not in block, name
+    assert seen >= 3
+
+
 def test_product_never_imports_the_oracle():
     for dp, _, files in os.walk(PKG):
         for f in files:
