@@ -28,6 +28,7 @@ class RPNPostProcessor(torch.nn.Module):
         self.box_coder = box_coder if box_coder is not None else BoxCoder(weights=(1.0, 1.0, 1.0, 1.0))
         self.fpn_post_nms_top_n = post_nms_top_n if fpn_post_nms_top_n is None else fpn_post_nms_top_n
         self.fpn_post_nms_per_batch = fpn_post_nms_per_batch
+        self.fused_select = True   # test hook: False sends the selection through the torch-op formulation
         self._seg_cache = {}
 
     # ---- reference :53-74 -------------------------------------------------------------
@@ -151,8 +152,12 @@ class RPNPostProcessor(torch.nn.Module):
         else:
             small = None
 
-        fused_select = (self.nms_thresh > 0 and small is None and num_levels > 1 and
-                        not (self.training and self.fpn_post_nms_per_batch))
+        # the batched NMS + b200_select_topk serve every case but the per-batch top-k of FPN training (reference
+        # :161-172) and min_size > 0: several levels in test mode (:173-180), and the single feature map of the
+        # reference's shipped C4 configs in both modes, where the result is simply each image's kept boxes in
+        # score order (:111-122 -- select_over_all_levels is skipped, :148-150)
+        fused_select = (self.fused_select and self.nms_thresh > 0 and small is None and
+                        not (num_levels > 1 and self.training and self.fpn_post_nms_per_batch))
         if fused_select:
             per_img = sum(min(k, self.post_nms_top_n) if self.post_nms_top_n > 0 else k for k in ks)
             fused_select = per_img <= 16384
@@ -160,7 +165,7 @@ class RPNPostProcessor(torch.nn.Module):
             # NMS for all (image, level) segments, then the per-image top-k over levels
             # (reference :173-180) in one more kernel; one host sync for the counts
             keep_idx, keep_cnt = nms_batched(boxes, score, seg_off, self.nms_thresh, self.post_nms_top_n, max(ks))
-            k2 = min(self.fpn_post_nms_top_n, K)
+            k2 = min(self.fpn_post_nms_top_n, K) if num_levels > 1 else per_img
             rois, sc, cnt = select_topk(boxes, score, seg_off, keep_idx, keep_cnt, n_img, k2, per_img)
             n_keep = cnt.tolist()
             results = []

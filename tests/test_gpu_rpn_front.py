@@ -121,3 +121,30 @@ def test_rpn_postprocessor_fused_front_equals_torch_front(min_size):
         gb, _ = _canon(f.bbox, f.get_field("objectness"))
         wb, _ = _canon(p.bbox, p.get_field("objectness"))
         np.testing.assert_allclose(gb, wb, atol=1e-3, rtol=0)
+
+
+@pytest.mark.parametrize("training", [False, True])
+@pytest.mark.parametrize("post_nms", [150, 2000])
+def test_rpn_postprocessor_single_level_selection_is_fused(training, post_nms):
+    """The reference's shipped configs are C4: ONE feature map, no cross-level top-k (rpn/inference.py:148-150).  The
+    batched NMS + b200_select_topk path must return what the torch-op formulation returns: each image's kept boxes
+    in score order, at most post_nms_top_n of them; in training the ground-truth boxes are appended (:53-74)."""
+    from cvpr22_cross_modal_pseudo_labeling_b200.modeling import RPNPostProcessor
+    from cvpr22_cross_modal_pseudo_labeling_b200.structures import BoxList
+    anchors, obj, reg = _levels(2, 3, [(50, 84)])
+    pp = RPNPostProcessor(3000, post_nms, 0.7, 0)
+    pp.train(training)
+    targets = None
+    if training:
+        targets = [BoxList(torch.tensor([[10., 20., 200., 300.], [50., 60., 400., 450.]], device="cuda"), a[0].size)
+                   for a in anchors]
+    fused = pp(anchors, obj, reg, targets)
+    pp.fused_select = False
+    plain = pp(anchors, obj, reg, targets)
+    for f, p in zip(fused, plain):
+        assert len(f) == len(p) > 0
+        assert len(f) <= post_nms + (2 if training else 0)
+        assert torch.equal(f.get_field("objectness"), p.get_field("objectness"))
+        assert torch.equal(f.bbox, p.bbox)
+        s = f.get_field("objectness")[: len(f) - (2 if training else 0)]
+        assert bool((s[:-1] >= s[1:]).all())
