@@ -788,11 +788,19 @@ roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, const in
     if ((kProbe & 2)) st.bar1 += clock64() - t0;
     if (tid == 0 && !(flags & 1)) bulk_s2g(out + (size_t)r * kTileFloats, smem_u32(tile), kTileFloats * 4, store_policy);
     if (out_mean && tid < kRC) {
+      // seven independent row sums, then their sum: a 49-long dependent chain of additions held eight of the
+      // fourteen consumer warps back for ~300 cycles per RoI while the others waited at the next RoI's first
+      // flush (this kernel is the fast-math path: the order of an fp32 sum is free within its 1e-5)
       const float* row = tile + tid * kBins;
-      float s = 0.f;
-#pragma unroll 7
-      for (int j = 0; j < kBins; ++j) s = __fadd_rn(s, row[j]);
-      out_mean[(size_t)r * kRC + tid] = __fdiv_rn(s, (float)kBins);
+      float rs[kP];
+#pragma unroll
+      for (int b = 0; b < kP; ++b) rs[b] = row[b * kP];
+#pragma unroll
+      for (int j = 1; j < kP; ++j)
+#pragma unroll
+        for (int b = 0; b < kP; ++b) rs[b] += row[b * kP + j];
+      const float s = ((rs[0] + rs[1]) + (rs[2] + rs[3])) + ((rs[4] + rs[5]) + rs[6]);
+      out_mean[(size_t)r * kRC + tid] = s * (1.0f / (float)kBins);
     }
   }
   if (tid == 0) bulk_wait_all();  // the last store must have left shared memory before the CTA exits
