@@ -154,6 +154,7 @@ def debug_nms(force_bitmask=False):
     lib().b200_debug_nms(int(force_bitmask))
 
 
-def debug_bwd(force_generic=False):
-    """Test hook: force the per-tap RoIAlign backward instead of the marching kernel."""
-    lib().b200_debug_bwd(int(force_generic))
+def debug_bwd(mode=0):
+    """Test hook: the RoIAlign backward kernel for NHWC / sampling ratio 2 -- 0 (or False) = the marching kernel by
+    tap row (default), 1 (or True) = the per-tap kernel, 2 = the marching kernel by output row (round 1)."""
+    lib().b200_debug_bwd(int(mode))

@@ -233,12 +233,191 @@ roi_align_bwd_march(const LevelGradTable lt, int C, const float* __restrict__ ro
   }
 }
 
-bool g_bwd_force_generic = false;
+// ---------------------------------------------------------------------------------------
+// Marching backward BY TAP ROW (the default for NHWC, sampling ratio 2).  roi_align_bwd_march above gives a thread
+// one OUTPUT row: every output row reduces into its own (up to four) tap rows, so a tap row that feeds two or three
+// output rows -- every one at 14 x 14, where samples lie 0.5-1 pixel apart -- is reduced into two or three times.  The
+// kernel is bound by the L2's reduction rate ("RoIAlign backward"), so those bytes are the time.  Here a
+// thread owns (4 channels, one DISTINCT tap row): the gradient of its row is first gathered over the output rows
+// that touch it, top(pw) = sum_ph wy[row][ph] * g[ph][pw] (shared-memory reads of the staged gradient tile), the same
+// x march spreads it over the tap columns, and every (RoI, tap pixel, channel quad) leaves as exactly ONE
+// red.global.add.v4.f32.  kCA chunks of 64 channels are staged at once; the work items (chunk, tap row, quad) are
+// dealt out flat, so that 16 * kCA consecutive threads reduce into 256 * kCA contiguous bytes of one pixel.
+// The addends are the reference's (top * w_y * w_x) / count summed per (RoI, pixel) before they reach memory.
+// ---------------------------------------------------------------------------------------
+constexpr int kMaxTapRows = 2 * kMaxAxisSamples;  // distinct tap rows of a RoI, at most (two per y sample)
+constexpr int kTapRowPH = 16;                     // PH <= 16
+
+struct __align__(16) TapRowTables {
+  int rowofs[kMaxTapRows];         // element offset y * W * C of distinct tap row i (ascending y)
+  int phr[kMaxTapRows];            // first | last << 8 output row with a weight on row i (first > last: none)
+  float wy[kMaxTapRows][kTapRowPH];  // weight x 1/count of tap row i for output row ph
+  int nrows;
+};
+
+// one warp: the distinct tap rows of the RoI's 2 * PH y samples (PH <= 16) and their weights per output row
+__device__ __forceinline__ void build_taprow_tables(const RoiGeom& g, int PH, int H, int W, int C, int lane,
+                                                    TapRowTables* tt) {
+  float4* z = reinterpret_cast<float4*>(&tt->wy[0][0]);
+  for (int i = lane; i < kMaxTapRows * kTapRowPH / 4; i += 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int ns = 2 * PH;
+  bool ok = false;
+  AxisTap t;
+  t.lo = t.hi = 0;
+  t.l = t.h = 0.f;
+  if (lane < ns) t = axis_sample(g.start_h, lane >> 1, g.bin_h, lane & 1, 2, H, ok);
+  ok = ok && lane < ns;
+  // sample positions ascend with the lane, so do lo and hi, and the out-of-range samples sit at the two ends: a
+  // sample's rows are new iff they lie above the previous valid sample's hi row
+  const int phi = __shfl_up_sync(0xffffffffu, t.hi, 1);
+  const bool pok = __shfl_up_sync(0xffffffffu, (int)ok, 1) != 0;
+  const int pmax = (lane > 0 && pok) ? phi : -1;
+  const bool new_lo = ok && t.lo > pmax, new_hi = ok && t.hi > pmax && t.hi != t.lo;
+  int scan = (int)new_lo + (int)new_hi;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, scan, d);
+    if (lane >= d) scan += v;
+  }
+  const int nrows = __shfl_sync(0xffffffffu, scan, 31);
+  const int jhi = scan - 1, jlo = t.lo == t.hi ? jhi : jhi - 1;  // (hi is the highest row listed so far)
+  if (new_hi) tt->rowofs[jhi] = t.hi * W * C;
+  if (new_lo) tt->rowofs[jlo] = t.lo * W * C;
+  __syncwarp();  // the matrix is zeroed
+  // the two samples of an output row may meet in one matrix element: even samples first, then the odd ones
+#pragma unroll
+  for (int par = 0; par < 2; ++par) {
+    if (ok && (lane & 1) == par) {
+      const int ph = lane >> 1;
+      tt->wy[jlo][ph] += 0.25f * t.h;  // (lo == hi, a sample clamped to the border: both weights on the one row)
+      tt->wy[jhi][ph] += 0.25f * t.l;
+    }
+    __syncwarp();
+  }
+  for (int i = lane; i < nrows; i += 32) {
+    int first = PH, last = -1;
+    for (int ph = 0; ph < PH; ++ph)
+      if (tt->wy[i][ph] != 0.f) {
+        first = min(first, ph);
+        last = ph;
+      }
+    tt->phr[i] = last < 0 ? (1 | (0 << 8)) : (first | (last << 8));
+  }
+  if (lane == 0) tt->nrows = nrows;
+}
+
+template <int kThreads, int kMinBlocks, int kCA>
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
+roi_align_bwd_taprow(const LevelGradTable lt, int C, const float* __restrict__ rois, const int32_t* __restrict__ order,
+                     int PH, int PW, int groups_per_cta, const float* __restrict__ grad_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int NB = PH * PW;
+  const bool swz = (NB & 3) == 0;
+  const int tile_floats = kChunkB * NB + kTilePadFloats;
+  float* g_s = reinterpret_cast<float*>(smem_raw);
+  AxisEntry* ytab = reinterpret_cast<AxisEntry*>(smem_raw + sizeof(float) * kCA * tile_floats);
+  XSample* xs = reinterpret_cast<XSample*>(ytab + kMaxAxisSamples);
+  int* colofs = reinterpret_cast<int*>(xs + kMaxAxisSamples + 1);
+  __shared__ int ncols_s;
+  __shared__ TapRowTables tt;
+
+  const int tid = threadIdx.x;
+  const int cta_channels = kChunkB * kCA * groups_per_cta;
+  const int ctas_per_roi = C / cta_channels;
+  // `order` (optional): consecutive CTAs take RoIs that are neighbours in one feature map
+  const long long r = order ? (long long)order[blockIdx.x / ctas_per_roi] : (long long)(blockIdx.x / ctas_per_roi);
+  const int c0 = (blockIdx.x % ctas_per_roi) * cta_channels;
+  const float* p = rois + r * 5;
+  const int batch = (int)p[0];
+  const float x1 = p[1], y1 = p[2], x2 = p[3], y2 = p[4];
+  const int level = lt.n_levels == 1 ? 0 : fpn_level(x1, y1, x2, y2, lt.k_min, lt.k_max);
+  if (level < 0) return;
+  const int H = lt.H[level], W = lt.W[level];
+  const RoiGeom g = roi_geometry(x1, y1, x2, y2, lt.scale[level], PH, PW, 2);
+  const int warp = tid >> 5, lane = tid & 31;
+  build_sep_tables(g, PH, PW, H, W, C, warp, lane, ytab, xs, colofs, &ncols_s);  // (warp 1: the column tables)
+  if (warp == 2) build_taprow_tables(g, PH, H, W, C, lane, &tt);
+  __syncthreads();
+
+  const int ncols = ncols_s, nrows = tt.nrows;
+  constexpr int kQ = kChunkB / 4;  // channel quads of a chunk
+  char* img = reinterpret_cast<char*>(lt.data[level] + (size_t)batch * H * W * C);
+  const uint32_t xs_a = smem_u32(xs), co_a = smem_u32(colofs), g0_a = smem_u32(g_s), wy_a = smem_u32(&tt.wy[0][0]);
+  const uint32_t nb4 = 4u * (uint32_t)NB;
+
+  for (int gg = 0; gg < groups_per_cta; ++gg) {
+    const int c_begin = c0 + gg * kCA * kChunkB;
+    if (gg > 0) __syncthreads();  // everyone is done reading the previous group's tiles
+#pragma unroll
+    for (int ca = 0; ca < kCA; ++ca)
+      tile_copy_in(g_s + ca * tile_floats, grad_out + ((size_t)r * C + c_begin + ca * kChunkB) * NB, NB, swz, tid, kThreads);
+    __syncthreads();
+    for (int u = tid; u < nrows * kQ * kCA; u += kThreads) {
+      const int qc = u % (kQ * kCA), i = u / (kQ * kCA);
+      const int ca = qc / kQ, q = qc % kQ;
+      const int phr = tt.phr[i];
+      const int ph_lo = phr & 0xff, ph_hi = phr >> 8;
+      if (ph_lo > ph_hi) continue;
+      char* rp = img + 4 * (size_t)(c_begin + ca * kChunkB + 4 * q + tt.rowofs[i]);
+      // this thread's four channel rows of the staged gradient tile, and its row of the weight matrix
+      const uint32_t g_a = g0_a + 4u * (uint32_t)(ca * tile_floats + tile_row(4 * q, NB, swz));
+      const uint32_t w_a = wy_a + 4u * (uint32_t)(i * kTapRowPH);
+      float4 t[2];
+      t[0] = t[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 top = make_float4(0.f, 0.f, 0.f, 0.f);
+      int s = 0;
+      float4 e = lds128b(xs_a);  // (jhi, l, h, -)
+      for (int j0 = 0; j0 < ncols; j0 += 2) {
+#pragma unroll
+        for (int uu = 0; uu < 2; ++uu) {
+          const int j = j0 + uu;
+          if (j < ncols) {
+            // samples whose right tap column is j: they add to columns j-1 (t[uu^1]) and j (t[uu])
+            while (__float_as_int(e.x) == j) {
+              if (!(s & 1)) {
+                // the row's gradient for output column pw = s / 2, gathered over the output rows that touch it
+                top = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int ph = ph_lo; ph <= ph_hi; ++ph) {
+                  const float wv = ldsf(w_a + 4u * (uint32_t)ph);
+                  const uint32_t ga = g_a + 4u * (uint32_t)(ph * PW + (s >> 1));
+                  top.x = fmaf(wv, ldsf(ga), top.x);
+                  top.y = fmaf(wv, ldsf(ga + nb4), top.y);
+                  top.z = fmaf(wv, ldsf(ga + 2u * nb4), top.z);
+                  top.w = fmaf(wv, ldsf(ga + 3u * nb4), top.w);
+                }
+              }
+              t[uu ^ 1].x = fmaf(e.z, top.x, t[uu ^ 1].x);
+              t[uu ^ 1].y = fmaf(e.z, top.y, t[uu ^ 1].y);
+              t[uu ^ 1].z = fmaf(e.z, top.z, t[uu ^ 1].z);
+              t[uu ^ 1].w = fmaf(e.z, top.w, t[uu ^ 1].w);
+              t[uu].x = fmaf(e.y, top.x, t[uu].x);
+              t[uu].y = fmaf(e.y, top.y, t[uu].y);
+              t[uu].z = fmaf(e.y, top.z, t[uu].z);
+              t[uu].w = fmaf(e.y, top.w, t[uu].w);
+              ++s;
+              e = lds128b(xs_a + 16u * (uint32_t)s);
+            }
+            // column j-1 is complete: nothing right of column j's samples touches it
+            if (j > 0) {
+              const float4 v = t[uu ^ 1];
+              red_add_v4(reinterpret_cast<float*>(rp + lds32b(co_a + 4u * (uint32_t)(j - 1))), v.x, v.y, v.z, v.w);
+              t[uu ^ 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+        }
+      }
+      const float4 v = t[(ncols - 1) & 1];
+      red_add_v4(reinterpret_cast<float*>(rp + lds32b(co_a + 4u * (uint32_t)(ncols - 1))), v.x, v.y, v.z, v.w);
+    }
+  }
+}
+
+int g_bwd_mode = 0;  // test / tuning hook: 0 = tap-row march, 1 = per-tap kernel, 2 = output-row march
 
 }  // namespace
 }  // namespace b200
 
-extern "C" void b200_debug_bwd(int force_generic) { b200::g_bwd_force_generic = force_generic != 0; }
+extern "C" void b200_debug_bwd(int mode) { b200::g_bwd_mode = mode; }
 
 extern "C" int b200_roi_align_backward(const b200_level_grad* levels, int n_levels, int layout, int batch,
                                        int channels, const float* rois, int64_t n_rois, int pooled_h,
@@ -275,7 +454,7 @@ extern "C" int b200_roi_align_backward_ws(const b200_level_grad* levels, int n_l
   lt.k_max = -log2f(levels[n_levels - 1].spatial_scale);
   const int NB = pooled_h * pooled_w;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (!g_bwd_force_generic && layout == B200_LAYOUT_NHWC && sampling_ratio == 2 && pooled_h <= 16 && pooled_w <= 16 &&
+  if (g_bwd_mode != 1 && layout == B200_LAYOUT_NHWC && sampling_ratio == 2 && pooled_h <= 16 && pooled_w <= 16 &&
       channels % kChunkB == 0 && aligned16(grad_out)) {
     const int n_chunks = channels / kChunkB;
     int cpc = n_chunks % 4 == 0 ? 4 : (n_chunks % 2 == 0 ? 2 : 1);
@@ -301,6 +480,37 @@ extern "C" int b200_roi_align_backward_ws(const b200_level_grad* levels, int n_l
       order = static_cast<int32_t*>(workspace);
       int rc = launch_roi_order(flt, rois, n_rois, order, st);
       if (rc != B200_OK) return rc;
+    }
+    if (g_bwd_mode != 2) {
+      // by tap row.  7 x 7: all four chunks of a 256-channel RoI staged at once (50 KB), 14 x 14: one chunk (50 KB)
+      const size_t tables = kMaxAxisSamples * sizeof(AxisEntry) + (kMaxAxisSamples + 1) * sizeof(XSample) + kMaxCols * sizeof(int);
+      if (NB <= 64) {
+        const int ca = n_chunks % 4 == 0 ? 4 : 1;
+        const size_t sm = sizeof(float) * ca * (kChunkB * NB + kTilePadFloats) + tables;
+        const int64_t grid2 = n_rois * (n_chunks / ca);
+        if (ca == 4) {
+          auto kern = roi_align_bwd_taprow<256, 4, 4>;
+          static SmemHighWater hw;
+          int rc = ensure_dynamic_smem(kern, sm, &hw, "roi_align_bwd: smem attribute");
+          if (rc != B200_OK) return rc;
+          kern<<<(unsigned)grid2, 256, sm, st>>>(lt, channels, rois, order, pooled_h, pooled_w, 1, grad_out);
+        } else {
+          auto kern = roi_align_bwd_taprow<256, 4, 1>;
+          static SmemHighWater hw;
+          int rc = ensure_dynamic_smem(kern, sm, &hw, "roi_align_bwd: smem attribute");
+          if (rc != B200_OK) return rc;
+          kern<<<(unsigned)grid2, 256, sm, st>>>(lt, channels, rois, order, pooled_h, pooled_w, 1, grad_out);
+        }
+      } else {
+        const size_t sm = sizeof(float) * (kChunkB * NB + kTilePadFloats) + tables;
+        auto kern = roi_align_bwd_taprow<256, 4, 1>;
+        static SmemHighWater hw;
+        int rc = ensure_dynamic_smem(kern, sm, &hw, "roi_align_bwd: smem attribute");
+        if (rc != B200_OK) return rc;
+        kern<<<(unsigned)grid, 256, sm, st>>>(lt, channels, rois, order, pooled_h, pooled_w, cpc, grad_out);
+      }
+      B200_CHECK_LAUNCH("roi_align_bwd_taprow");
+      return B200_OK;
     }
     if (pooled_h <= 8) {
       auto kern = roi_align_bwd_march<128, 8>;

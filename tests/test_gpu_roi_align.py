@@ -216,12 +216,13 @@ def test_pooler_multilevel_matches_oracle(nhwc, res):
     assert np.array_equal(got.cpu().numpy(), want)
 
 
-@pytest.fixture(params=["march", "generic"])
+@pytest.fixture(params=["march", "generic", "march_by_output_row"])
 def bwd_path(request):
-    """Backward runs on the marching kernel (NHWC, sampling_ratio 2) and on the per-tap kernel."""
-    _ext().debug_bwd(request.param == "generic")
+    """Backward runs on the marching kernel by tap row (NHWC, sampling_ratio 2: the default), on the per-tap kernel
+    and on the round-1 marching kernel by output row."""
+    _ext().debug_bwd({"march": 0, "generic": 1, "march_by_output_row": 2}[request.param])
     yield request.param
-    _ext().debug_bwd(False)
+    _ext().debug_bwd(0)
 
 
 @pytest.mark.parametrize("nhwc", [False, True])
