@@ -15,7 +15,9 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:tc_g
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:tc_gemm -s 2 -c 1 -f -o gpurun_out/final_tc_gemm_linear_emb_pred python scripts/ncu_match.py linear > /dev/null 2>&1
 # backward (not part of the inference step) and the bf16 forward
 for res in 7 14; do
-  timeout 300 ncu --set full --clock-control none --import-source on -k regex:roi_align_bwd_march -s 1 -c 1 -f -o gpurun_out/final_roi_align_bwd_march_$res python scripts/ncu_bwd.py $res > /dev/null 2>&1
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:roi_align_bwd_taprow -s 1 -c 1 -f -o gpurun_out/final_roi_align_bwd_taprow_$res python scripts/ncu_bwd.py $res > /dev/null 2>&1
 done
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:roi_align_fwd_rows -s 1 -c 1 -f -o gpurun_out/final_roi_align_fwd_rows_bf16 python scripts/ncu_rows2.py 0 step bf16 > /dev/null 2>&1
+# the tiled gather at BASELINE config #1 (the reference's shipped C4 pooler)
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:roi_align_fwd_tile -s 3 -c 1 -f -o gpurun_out/final_roi_align_fwd_tile python scripts/perf_config1.py 0 > /dev/null 2>&1
 ls -la gpurun_out | head -40
