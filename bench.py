@@ -463,7 +463,7 @@ def roofline_passes(torch, dev, feats, scales, shapes, state, cand_boxes, cand_s
     out.append(hbm_entry("nms_fused (RPN, 80 segments, keep 1000)", bm_bytes, ms, convention="materialised 64x64 bitmask (SURVEY 8d)",
                          boxes_per_s=float(lens.sum() / ms * 1e3), segments=int(len(lens))))
     ms = timeit(lambda: nms_batched(cand_boxes, cand_scores, seg_off, 0.7, -1, max(RPN_LENS)), iters=3)
-    out.append(hbm_entry("nms_fused (RPN, 80 segments, keep all)", bm_bytes, ms, convention="materialised 64x64 bitmask (SURVEY 8d)",
+    out.append(hbm_entry("nms (RPN, 80 segments, keep all: bitmask path)", bm_bytes, ms, convention="materialised 64x64 bitmask (SURVEY 8d)",
                          pair_tests_per_s=float(np.sum(lens * (lens - 1) / 2) / ms * 1e3)))
     # box-head per-class NMS: 16 images x 65 classes, candidates = prob > 0.05 of the step's scores (thr 0.5)
     try:

@@ -148,10 +148,11 @@ def debug_match(legacy=False):
     lib().b200_debug_match(int(legacy))
 
 
-def debug_nms(force_bitmask=False):
-    """Test hook: force the three-kernel bitmask NMS path (default: fused kernel when the
-    longest segment fits in shared memory)."""
-    lib().b200_debug_nms(int(force_bitmask))
+def debug_nms(mode=0):
+    """Test hook: 0 (or False) = the library's choice (fused one-CTA-per-segment kernel when the longest segment fits
+    in shared memory, except keep-all calls over long segments, which take the bitmask path), 1 (or True) = force the
+    three-kernel bitmask path, 2 = force the fused kernel wherever it fits."""
+    lib().b200_debug_nms(int(mode))
 
 
 def debug_bwd(mode=0):

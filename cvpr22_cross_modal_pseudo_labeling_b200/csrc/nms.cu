@@ -699,6 +699,7 @@ nms_fused_kernel(const float4* __restrict__ boxes, const float* __restrict__ sco
 }
 
 bool g_nms_force_bitmask = false;
+int g_nms_force_fused = 0;
 
 // dynamic shared memory of the fused kernel: boxes, and for the early-stopping mode the kept list
 // (box, area, x centre/reach) plus the per-chunk x-order (sort keys + permutation)
@@ -710,8 +711,14 @@ size_t fused_smem_bytes(size_t n_cap, size_t kl_cap) {
 }
 
 // the fused kernel needs the segment's boxes (+ the kept list) in one CTA's shared memory
-bool fused_applies(int64_t max_seg_len, int64_t max_keep) {
+bool fused_applies(int64_t max_seg_len, int64_t max_keep, int64_t n_total, int64_t n_segments) {
   if (g_nms_force_bitmask || max_seg_len > kFusedMaxSeg) return false;
+  // keep-all over long segments (layers.nms / boxlist_nms without max_proposals on RPN-sized inputs): the push sweep
+  // of the fused kernel tests every kept box against every later live box from ONE CTA per segment, the bitmask path
+  // spreads the same pair tests over (segment, 64 x 64 tile) CTAs -- measured 1.5-2.4 x faster from 500 to 6000 boxes
+  // per segment (scripts/perf_nms_keepall.py).  Many short segments (the box head's per-class lists) stay fused: the
+  // bitmask grid is sized by the LONGEST segment.
+  if (g_nms_force_fused == 0 && max_keep <= 0 && max_seg_len >= 512 && n_total >= 384 * n_segments) return false;
   const size_t n_cap = (size_t)b200::ceil_div<int64_t>(max_seg_len, kTile) * kTile;
   const size_t kl_cap = max_keep > 0 ? (size_t)(max_keep < max_seg_len ? max_keep : max_seg_len) + kTile : 0;
   return fused_smem_bytes(n_cap, kl_cap) + 10 * 1024 <= 227 * 1024;
@@ -877,7 +884,10 @@ extern "C" int b200_debug_nms_stats(long long* host_out) {
 }
 #endif
 
-extern "C" void b200_debug_nms(int force_bitmask) { g_nms_force_bitmask = force_bitmask != 0; }
+extern "C" void b200_debug_nms(int mode) {  // 0 = default choice, 1 = bitmask path, 2 = fused kernel wherever it fits
+  g_nms_force_bitmask = mode == 1;
+  g_nms_force_fused = mode == 2 ? 1 : 0;
+}
 
 extern "C" size_t b200_nms_workspace_bytes(int64_t n_total, int64_t n_segments, int64_t max_seg_len) {
   if (n_total < 0 || n_segments < 0 || max_seg_len < 0) return 0;
@@ -912,7 +922,7 @@ extern "C" int b200_nms_batched(const float* boxes, const float* scores, const i
   // kept-box list for the early-stopping sweep (only when max_keep is given)
   const int kl_cap = max_keep > 0 ? (int)(max_keep < max_seg_len ? max_keep : max_seg_len) + kTile : 0;
   const size_t smem = fused_smem_bytes((size_t)n_cap, (size_t)kl_cap);
-  if (fused_applies(max_seg_len, max_keep)) {
+  if (fused_applies(max_seg_len, max_keep, n_total, n_segments)) {
     if (max_seg_len <= 1024) {
       auto kern = nms_fused_kernel<256>;
       static SmemHighWater hw;

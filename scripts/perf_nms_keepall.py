@@ -37,12 +37,12 @@ for n in (500, 1000, 2000, 3000, 4000, 6000):
     scores = torch.from_numpy(np.concatenate([cs[o:o + k] for o, k in segs])).cuda()
     seg_off = torch.from_numpy(np.arange(len(segs) + 1, dtype=np.int32) * n).cuda()
     out = {}
-    for name, force in (("fused", False), ("bitmask", True)):
+    for name, force in (("fused", 2), ("bitmask", 1)):
         _ext.debug_nms(force)
         out[name] = timeit(lambda: nms_batched(boxes, scores, seg_off, 0.7, -1, n))
         ki, kc = nms_batched(boxes, scores, seg_off, 0.7, -1, n)
         out[name + "_kept"] = int(kc.sum().item())
-    _ext.debug_nms(False)
+    _ext.debug_nms(0)
     auto = timeit(lambda: nms_batched(boxes, scores, seg_off, 0.7, -1, n))
     print("keep-all, %d segments x %5d boxes: fused %.3f ms, bitmask %.3f ms, default %.3f ms (kept %d / %d)" %
           (len(segs), n, out["fused"], out["bitmask"], auto, out["fused_kept"], out["bitmask_kept"]), flush=True)

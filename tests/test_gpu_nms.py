@@ -14,9 +14,9 @@ def nms_path(request):
     """Every test runs on both device paths: the fused shared-memory kernel and the
     three-kernel 64x64 bitmask + sweep path (used for segments > 13952 boxes)."""
     from cvpr22_cross_modal_pseudo_labeling_b200 import _ext
-    _ext.debug_nms(request.param == "bitmask")
+    _ext.debug_nms(1 if request.param == "bitmask" else 2)   # (2: the fused kernel wherever it fits)
     yield request.param
-    _ext.debug_nms(False)
+    _ext.debug_nms(0)
 
 
 def _gpu_nms(boxes, scores, thr):
