@@ -5,10 +5,12 @@
 // rounded exactly as the reference rounds it -- (top * w_k) / count, :239-242 -- only the
 // order of the additions (atomics there, atomics here) is free.
 //
-//   NHWC: a thread owns (4 channels, one bin); every tap is ONE 128-bit vector reduction
-//         (red.global.add.v4.f32) instead of four scalar atomics.
-//   NCHW: a thread owns (channel, bin) with scalar reductions, bins fastest so that the
-//         reads of grad_out are coalesced.
+//   roi_align_bwd_taprow  NHWC, sampling ratio 2 (the default for the FPN poolers): a thread owns (4 channels, one
+//         distinct tap row), one red.global.add.v4.f32 per (RoI, tap pixel, quad); see the comment at the kernel.
+//   roi_align_bwd_march   the round-1 formulation, a thread per output row (b200_debug_bwd(2), tests).
+//   roi_align_bwd_generic any sampling ratio / layout.  NHWC: a thread owns (4 channels, one bin); every tap is ONE
+//         128-bit vector reduction instead of four scalar atomics.  NCHW: a thread owns (channel, bin) with scalar
+//         reductions, bins fastest so that the reads of grad_out are coalesced.
 #include "roi_align_fwd.cuh"
 
 namespace b200 {

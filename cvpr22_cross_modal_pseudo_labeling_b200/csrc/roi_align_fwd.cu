@@ -4,7 +4,10 @@
 // per-level _C.roi_align_forward (csrc/cpu/ROIAlign_cpu.cpp:114-217,
 // csrc/cuda/ROIAlign_cuda.cu:65-122) and the scatter back, in one launch.
 //
-// Two kernels:
+// Three kernels here (the separable and the row-streaming fast-math kernels live in roi_align_fwd_sep.cu /
+// roi_align_fwd_rows.cu):
+//   roi_align_fwd_tile    NHWC features, ANY sampling ratio (the reference's shipped C4 pooler: 1024 channels,
+//       14 x 14 bins, adaptive sampling): gather with per-CTA axis tables and a shared output tile, see below.
 //   roi_align_fwd_march   NHWC features, sampling_ratio 2 (the FPN box / mask poolers).
 //       One CTA per (RoI, 64-channel chunk).  Sample geometry is computed once per CTA
 //       into two small axis tables.  A thread owns (4 channels, one output row of bins)
@@ -169,9 +172,117 @@ constexpr int kTileThreads = 256;
 constexpr int kTileMaxAx = 128;  // samples per axis held in the tables (PH * grid_h, PW * grid_w)
 
 struct __align__(16) TileTap {
-  int lo, hi;  // element offsets of the two taps: y * W * C (rows), x * C (columns)
-  float l, h;  // their weights; both 0: the sample is out of range and contributes nothing
+  uint32_t lo, hi;  // BYTE offsets of the two taps inside the image's map: y * W * C * 4 (rows), x * C * 4 (columns)
+  float l, h;       // their weights; both 0: the sample is out of range and contributes nothing
 };
+
+// one sample of a bin: four 128-bit taps, the reference's order ((w1 v1 + w2 v2) + w3 v3) + w4 v4 added to the bin's
+// accumulator.  Two fp32 lanes per issue slot where possible (FMUL2 / FADD2 / FFMA2 round each lane like the scalar
+// instruction); one 64-bit base pointer + 32-bit byte offsets (the compiler spent three integer instructions per load
+// on 64-bit address arithmetic with element offsets).
+template <bool kExact>
+__device__ __forceinline__ void tile_sample(const char* __restrict__ base, const TileTap& ty, const TileTap& tx,
+                                            float2& acc_lo, float2& acc_hi) {
+  const float4 v1 = __ldg(reinterpret_cast<const float4*>(base + (ty.lo + tx.lo)));
+  const float4 v2 = __ldg(reinterpret_cast<const float4*>(base + (ty.lo + tx.hi)));
+  const float4 v3 = __ldg(reinterpret_cast<const float4*>(base + (ty.hi + tx.lo)));
+  const float4 v4 = __ldg(reinterpret_cast<const float4*>(base + (ty.hi + tx.hi)));
+  const float2 txhl = make_float2(tx.h, tx.l);
+  const float2 w12 = __fmul2_rn(make_float2(ty.h, ty.h), txhl), w34 = __fmul2_rn(make_float2(ty.l, ty.l), txhl);
+  const float2 w1 = make_float2(w12.x, w12.x), w2 = make_float2(w12.y, w12.y), w3 = make_float2(w34.x, w34.x),
+               w4 = make_float2(w34.y, w34.y);
+  if (kExact) {
+    // products as FMUL2, the three sums as scalar FADDs: ptxas (12.9) contracts mul.rn.f32x2 + add.rn.f32x2 into
+    // FFMA2 although both carry an explicit rounding mode (it never does for the scalar forms), which would
+    // break the bit-exactness; the accumulation below has no product operand and stays a FADD2
+    const float2 p1l = __fmul2_rn(w1, make_float2(v1.x, v1.y)), p1h = __fmul2_rn(w1, make_float2(v1.z, v1.w));
+    const float2 p2l = __fmul2_rn(w2, make_float2(v2.x, v2.y)), p2h = __fmul2_rn(w2, make_float2(v2.z, v2.w));
+    const float2 p3l = __fmul2_rn(w3, make_float2(v3.x, v3.y)), p3h = __fmul2_rn(w3, make_float2(v3.z, v3.w));
+    const float2 p4l = __fmul2_rn(w4, make_float2(v4.x, v4.y)), p4h = __fmul2_rn(w4, make_float2(v4.z, v4.w));
+    float2 s_lo, s_hi;
+    s_lo.x = __fadd_rn(__fadd_rn(__fadd_rn(p1l.x, p2l.x), p3l.x), p4l.x);
+    s_lo.y = __fadd_rn(__fadd_rn(__fadd_rn(p1l.y, p2l.y), p3l.y), p4l.y);
+    s_hi.x = __fadd_rn(__fadd_rn(__fadd_rn(p1h.x, p2h.x), p3h.x), p4h.x);
+    s_hi.y = __fadd_rn(__fadd_rn(__fadd_rn(p1h.y, p2h.y), p3h.y), p4h.y);
+    acc_lo = __fadd2_rn(acc_lo, s_lo);
+    acc_hi = __fadd2_rn(acc_hi, s_hi);
+  } else {
+    acc_lo = __ffma2_rn(w1, make_float2(v1.x, v1.y), acc_lo);
+    acc_hi = __ffma2_rn(w1, make_float2(v1.z, v1.w), acc_hi);
+    acc_lo = __ffma2_rn(w2, make_float2(v2.x, v2.y), acc_lo);
+    acc_hi = __ffma2_rn(w2, make_float2(v2.z, v2.w), acc_hi);
+    acc_lo = __ffma2_rn(w3, make_float2(v3.x, v3.y), acc_lo);
+    acc_hi = __ffma2_rn(w3, make_float2(v3.z, v3.w), acc_hi);
+    acc_lo = __ffma2_rn(w4, make_float2(v4.x, v4.y), acc_lo);
+    acc_hi = __ffma2_rn(w4, make_float2(v4.z, v4.w), acc_hi);
+  }
+}
+__device__ __forceinline__ bool tile_tap_valid(const TileTap& t) { return !(t.h == 0.f && t.l == 0.f); }  // (h = 1 - l > 0 or l > 0)
+
+// the bins of one thread.  GH / GW > 0: samples per bin and axis known at compile time (1 x 1 for two RoIs in three of
+// the C4 pooler, 2 x 2 for most of the rest): no sample loops; 0: taken from the geometry.
+template <bool kExact, int GH, int GW, int kSlots>
+__device__ __forceinline__ void tile_bins(const char* __restrict__ base, const TileTap* __restrict__ ytab,
+                                          const TileTap* __restrict__ xtab, int grid_h, int grid_w, int PW, int NB, int slot,
+                                          float* __restrict__ tile, int row0, int row1, int row2, int row3) {
+  const int gh = GH > 0 ? GH : grid_h, gw = GW > 0 ? GW : grid_w;
+  const int n_samples = gh * gw;
+  const float count = (float)n_samples;
+  // acc / count: a power-of-two count (1, 2, 4, 8, 16: nine RoIs in ten of the C4 pooler) is an exact scaling, so the
+  // product with 1 / count is the correctly rounded quotient as well; other counts take the IEEE division
+  const bool pow2 = (n_samples & (n_samples - 1)) == 0;
+  const float inv_count = __fdiv_rn(1.0f, count);
+  // (ph, pw) of the thread's bins without a division per bin
+  const int step_ph = kSlots / PW, step_pw = kSlots - step_ph * PW;
+  int ph = slot / PW, pw = slot - ph * PW;
+  for (int bin = slot; bin < NB; bin += kSlots) {
+    const TileTap* yt = ytab + ph * gh;
+    const TileTap* xt = xtab + pw * gw;
+    float2 acc_lo = make_float2(0.f, 0.f), acc_hi = make_float2(0.f, 0.f);
+    if (GH > 0 && GW > 0) {
+      TileTap ty[GH > 0 ? GH : 1], tx[GW > 0 ? GW : 1];
+#pragma unroll
+      for (int i = 0; i < GH; ++i) ty[i] = yt[i];
+#pragma unroll
+      for (int i = 0; i < GW; ++i) tx[i] = xt[i];
+#pragma unroll
+      for (int iy = 0; iy < GH; ++iy)
+#pragma unroll
+        for (int ix = 0; ix < GW; ++ix)
+          if (tile_tap_valid(ty[iy]) && tile_tap_valid(tx[ix])) tile_sample<kExact>(base, ty[iy], tx[ix], acc_lo, acc_hi);
+    } else {
+      for (int iy = 0; iy < gh; ++iy) {
+        const TileTap ty = yt[iy];
+        if (!tile_tap_valid(ty)) continue;
+        for (int ix = 0; ix < gw; ++ix) {
+          const TileTap tx = xt[ix];
+          if (!tile_tap_valid(tx)) continue;
+          tile_sample<kExact>(base, ty, tx, acc_lo, acc_hi);
+        }
+      }
+    }
+    if (GH == 1 && GW == 1) {
+      // (count 1: x / 1 = x)
+    } else if (pow2 || !kExact) {
+      const float2 ic = make_float2(inv_count, inv_count);
+      acc_lo = __fmul2_rn(acc_lo, ic);
+      acc_hi = __fmul2_rn(acc_hi, ic);
+    } else {
+      acc_lo = make_float2(__fdiv_rn(acc_lo.x, count), __fdiv_rn(acc_lo.y, count));
+      acc_hi = make_float2(__fdiv_rn(acc_hi.x, count), __fdiv_rn(acc_hi.y, count));
+    }
+    tile[row0 + bin] = acc_lo.x;
+    tile[row1 + bin] = acc_lo.y;
+    tile[row2 + bin] = acc_hi.x;
+    tile[row3 + bin] = acc_hi.y;
+    ph += step_ph;
+    pw += step_pw;
+    if (pw >= PW) {
+      pw -= PW;
+      ++ph;
+    }
+  }
+}
 
 // row of channel c in the [kCh x NB] tile: shifted by 4 floats per 8 channels when NB % 4 == 0 (as tile_row)
 template <int kCh>
@@ -227,97 +338,25 @@ roi_align_fwd_tile(const LevelTable lt, int C, const float* __restrict__ rois, i
     const int p = j / grid, k = j - p * grid;
     bool ok;
     const AxisTap t = is_y ? axis_sample(g.start_h, p, g.bin_h, k, grid, H, ok) : axis_sample(g.start_w, p, g.bin_w, k, grid, W, ok);
-    const int stride = is_y ? W * C : C;
+    const uint32_t stride = 4u * (uint32_t)(is_y ? W * C : C);  // (the launcher checks H * W * C * 4 < 2^32)
     TileTap e;
-    e.lo = ok ? t.lo * stride : 0;
-    e.hi = ok ? t.hi * stride : 0;
+    e.lo = ok ? (uint32_t)t.lo * stride : 0u;
+    e.hi = ok ? (uint32_t)t.hi * stride : 0u;
     e.l = ok ? t.l : 0.f;
     e.h = ok ? t.h : 0.f;
     (is_y ? ytab : xtab)[j] = e;
   }
   __syncthreads();
   const int q = tid % kQuads, slot = tid / kQuads;
-  const float* base = lt.data[h.level] + (size_t)h.batch * H * W * C + c_begin + 4 * q;
-  const int n_samples = g.grid_h * g.grid_w;
-  const float count = (float)n_samples;
-  // acc / count: a power-of-two count (1, 2, 4, 8, 16: nine RoIs in ten of the C4 pooler) is an exact scaling, so the
-  // product with 1 / count is the correctly rounded quotient as well; other counts take the IEEE division
-  const bool pow2 = (n_samples & (n_samples - 1)) == 0;
-  const float inv_count = __fdiv_rn(1.0f, count);
+  const char* base = reinterpret_cast<const char*>(lt.data[h.level] + (size_t)h.batch * H * W * C + c_begin + 4 * q);
   const int row0 = tile_row(4 * q, NB, swz), row1 = tile_row(4 * q + 1, NB, swz), row2 = tile_row(4 * q + 2, NB, swz),
             row3 = tile_row(4 * q + 3, NB, swz);
-  // (ph, pw) of the thread's bins without a division per bin
-  const int step_ph = kSlots / PW, step_pw = kSlots - step_ph * PW;
-  int ph = slot / PW, pw = slot - ph * PW;
-  for (int bin = slot; bin < NB; bin += kSlots) {
-    const TileTap* yt = ytab + ph * g.grid_h;
-    const TileTap* xt = xtab + pw * g.grid_w;
-    // two fp32 lanes per issue slot where possible (FMUL2 / FADD2 / FFMA2 round each lane like the scalar instruction;
-    // the exact mode keeps the reference's order ((w1 v1 + w2 v2) + w3 v3) + w4 v4, every operation rounded separately)
-    float2 acc_lo = make_float2(0.f, 0.f), acc_hi = make_float2(0.f, 0.f);
-    for (int iy = 0; iy < g.grid_h; ++iy) {
-      const TileTap ty = yt[iy];
-      if (ty.h == 0.f && ty.l == 0.f) continue;  // (a valid sample has h = 1 - l > 0 or l > 0)
-      const float* rlo = base + ty.lo;
-      const float* rhi = base + ty.hi;
-      const float2 tyh = make_float2(ty.h, ty.h), tyl = make_float2(ty.l, ty.l);
-      for (int ix = 0; ix < g.grid_w; ++ix) {
-        const TileTap tx = xt[ix];
-        if (tx.h == 0.f && tx.l == 0.f) continue;
-        const float4 v1 = __ldg(reinterpret_cast<const float4*>(rlo + tx.lo));
-        const float4 v2 = __ldg(reinterpret_cast<const float4*>(rlo + tx.hi));
-        const float4 v3 = __ldg(reinterpret_cast<const float4*>(rhi + tx.lo));
-        const float4 v4 = __ldg(reinterpret_cast<const float4*>(rhi + tx.hi));
-        const float2 txhl = make_float2(tx.h, tx.l);
-        const float2 w12 = __fmul2_rn(tyh, txhl), w34 = __fmul2_rn(tyl, txhl);  // (w1, w2), (w3, w4)
-        const float2 w1 = make_float2(w12.x, w12.x), w2 = make_float2(w12.y, w12.y), w3 = make_float2(w34.x, w34.x),
-                     w4 = make_float2(w34.y, w34.y);
-        if (kExact) {
-          // products as FMUL2, the three sums as scalar FADDs: ptxas (12.9) contracts mul.rn.f32x2 + add.rn.f32x2 into
-          // FFMA2 although both carry an explicit rounding mode (it never does for the scalar forms), which would
-          // break the bit-exactness; the accumulation below has no product operand and stays a FADD2
-          const float2 p1l = __fmul2_rn(w1, make_float2(v1.x, v1.y)), p1h = __fmul2_rn(w1, make_float2(v1.z, v1.w));
-          const float2 p2l = __fmul2_rn(w2, make_float2(v2.x, v2.y)), p2h = __fmul2_rn(w2, make_float2(v2.z, v2.w));
-          const float2 p3l = __fmul2_rn(w3, make_float2(v3.x, v3.y)), p3h = __fmul2_rn(w3, make_float2(v3.z, v3.w));
-          const float2 p4l = __fmul2_rn(w4, make_float2(v4.x, v4.y)), p4h = __fmul2_rn(w4, make_float2(v4.z, v4.w));
-          float2 s_lo, s_hi;
-          s_lo.x = __fadd_rn(__fadd_rn(__fadd_rn(p1l.x, p2l.x), p3l.x), p4l.x);
-          s_lo.y = __fadd_rn(__fadd_rn(__fadd_rn(p1l.y, p2l.y), p3l.y), p4l.y);
-          s_hi.x = __fadd_rn(__fadd_rn(__fadd_rn(p1h.x, p2h.x), p3h.x), p4h.x);
-          s_hi.y = __fadd_rn(__fadd_rn(__fadd_rn(p1h.y, p2h.y), p3h.y), p4h.y);
-          acc_lo = __fadd2_rn(acc_lo, s_lo);
-          acc_hi = __fadd2_rn(acc_hi, s_hi);
-        } else {
-          acc_lo = __ffma2_rn(w1, make_float2(v1.x, v1.y), acc_lo);
-          acc_hi = __ffma2_rn(w1, make_float2(v1.z, v1.w), acc_hi);
-          acc_lo = __ffma2_rn(w2, make_float2(v2.x, v2.y), acc_lo);
-          acc_hi = __ffma2_rn(w2, make_float2(v2.z, v2.w), acc_hi);
-          acc_lo = __ffma2_rn(w3, make_float2(v3.x, v3.y), acc_lo);
-          acc_hi = __ffma2_rn(w3, make_float2(v3.z, v3.w), acc_hi);
-          acc_lo = __ffma2_rn(w4, make_float2(v4.x, v4.y), acc_lo);
-          acc_hi = __ffma2_rn(w4, make_float2(v4.z, v4.w), acc_hi);
-        }
-      }
-    }
-    if (pow2 || !kExact) {
-      const float2 ic = make_float2(inv_count, inv_count);
-      acc_lo = __fmul2_rn(acc_lo, ic);
-      acc_hi = __fmul2_rn(acc_hi, ic);
-    } else {
-      acc_lo = make_float2(__fdiv_rn(acc_lo.x, count), __fdiv_rn(acc_lo.y, count));
-      acc_hi = make_float2(__fdiv_rn(acc_hi.x, count), __fdiv_rn(acc_hi.y, count));
-    }
-    tile[row0 + bin] = acc_lo.x;
-    tile[row1 + bin] = acc_lo.y;
-    tile[row2 + bin] = acc_hi.x;
-    tile[row3 + bin] = acc_hi.y;
-    ph += step_ph;
-    pw += step_pw;
-    if (pw >= PW) {
-      pw -= PW;
-      ++ph;
-    }
-  }
+  if (g.grid_h == 1 && g.grid_w == 1)
+    tile_bins<kExact, 1, 1, kSlots>(base, ytab, xtab, 1, 1, PW, NB, slot, tile, row0, row1, row2, row3);
+  else if (g.grid_h == 2 && g.grid_w == 2)
+    tile_bins<kExact, 2, 2, kSlots>(base, ytab, xtab, 2, 2, PW, NB, slot, tile, row0, row1, row2, row3);
+  else
+    tile_bins<kExact, 0, 0, kSlots>(base, ytab, xtab, g.grid_h, g.grid_w, PW, NB, slot, tile, row0, row1, row2, row3);
   __syncthreads();
   // the [kCh x NB] block is contiguous in the NCHW output: 128-bit streaming stores
   {
@@ -528,8 +567,10 @@ int launch_forward(const LevelTable& lt, int layout, int C, const float* rois, i
   }
   // NHWC, any sampling ratio: the tiled gather when the [32 x NB] tile fits (tuning: g_variant & 16384 = the plain
   // gather, & 8192 = 64 channels per CTA)
+  bool maps_fit_u32 = true;  // the tap tables hold 32-bit byte offsets inside one image's map
+  for (int l = 0; l < lt.n_levels; ++l) maps_fit_u32 = maps_fit_u32 && (uint64_t)lt.H[l] * lt.W[l] * C * 4 < ((uint64_t)1 << 32);
   if (!g_force_generic && !(g_variant & 16384) && layout == B200_LAYOUT_NHWC && C % kChunk == 0 && (NB * 32) % 4 == 0 &&
-      tile_kernel_smem<kChunk>(NB) <= (size_t)100 * 1024) {
+      tile_kernel_smem<kChunk>(NB) <= (size_t)100 * 1024 && maps_fit_u32) {
     if (g_variant & 8192) {
       auto kern = roi_align_fwd_tile<kExact, 64>;
       static SmemHighWater hw;

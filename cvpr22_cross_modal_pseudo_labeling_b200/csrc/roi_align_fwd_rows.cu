@@ -622,7 +622,7 @@ roi_align_fwd_rows(const LevelTable lt, const float* __restrict__ rois, const in
       __syncwarp();
       // my turn: after planner p - 1 placed RoI n - 1 (planner 0's first turn is free)
       t0 = (kProbe & 2) ? clock64() : 0;
-      mbar_wait(&place_turn[p], (uint32_t)((k & 1) ^ (p == 0 ? 1 : 0)));
+      if (p > 0 || k > 0) mbar_wait(&place_turn[p], (uint32_t)((k & 1) ^ (p == 0 ? 1 : 0)));
       if ((kProbe & 2)) s_turn += clock64() - t0;
       place_rows<kPxB>(tabs + ti, lane, &ring_state, full_a, idle_a);
       __syncwarp();
