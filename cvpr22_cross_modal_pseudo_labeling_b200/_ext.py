@@ -138,6 +138,8 @@ def debug_set(force_generic=False, exact=True, variant=0):
       bit 7     (128) two copy warps instead of four; bit 8 (256) output tile not stored
       bit 9     (512) cycle counters of who waits for whom (read back with b200_debug_rows_stats)
       bits 10-12 (1024 * k) ring entries per wait group (default: 1 for fp32 maps, 4 for bf16 maps)
+      bit 13    (8192) tiled gather (NHWC, sampling ratio != 2): 64 channels per tile instead of 32
+      bit 14    (16384) tiled gather off: the plain per-(quad, bin) gather
     Process-wide; tests and probes reset it to (False, True, 0)."""
     lib().b200_debug_set(int(force_generic), int(exact), int(variant))
 
