@@ -290,11 +290,20 @@ class ClockSampler(threading.Thread):
                 pass
             time.sleep(0.002)
 
+    def window_begin(self):
+        """Only what is sampled from here on is reported.  The thread is started BEFORE the warm-up: its first NVML
+        calls cost milliseconds when eight ranks make them at once, and inside a 17 ms timed region that showed up as
+        one 3 ms step (bench line at N = 8: 1.09 instead of 0.98 ms/step)."""
+        self.begin = len(self.samples)
+        self.reasons = set()
+
     def stop(self):
         self._stop_evt.set()
-        self.join(timeout=2)
-        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        if self.is_alive():
+            self.join(timeout=2)
+        mine = self.samples[getattr(self, "begin", 0):]
+        return {"sm_mhz": float(np.median(mine)) if mine else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(mine)}
 
 
 # --------------------------------------------------------------------------------------------
@@ -715,21 +724,27 @@ def run_gpu(args):
             if e is not None:
                 torch.cuda.current_stream().wait_event(e)
 
+    sampler = ClockSampler(local)
+    if not os.environ.get("B200_BENCH_NO_SAMPLER"):
+        sampler.start()
     for i in range(args.warmup):
         gather_overlapped(run_step(), i)
     drain_gathers()
     sync_all()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.window_begin()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]   # (diagnostic: per-step device times)
     t0.record()
     for i in range(args.steps):
         gather_overlapped(run_step(), i)
+        marks[i].record()
     drain_gathers()   # the timed region ends when the last records have arrived everywhere
     t1.record()
     sync_all()
     clocks = sampler.stop()
     ms_total = t0.elapsed_time(t1)
+    step_marks = [t0.elapsed_time(m) for m in marks]
+    step_ms = [b - a for a, b in zip([0.0] + step_marks[:-1], step_marks)]
 
     # sustained: the same step replayed back to back for >= --sustain seconds (the timed K steps above last
     # ~20 ms; this shows whether the number holds once clocks and power settle)
@@ -887,6 +902,8 @@ def run_gpu(args):
             "exact_math_value": (rois_per_step / ((ms_step - kms["pool7"] + kms.get("pool7_exact_math", kms["pool7"])) * 1e-3)
                                  if args.math == "fast" else None),
             "sustained": sustained,
+            "step_ms_rank0": {"first3": [round(v, 4) for v in step_ms[:3]], "median": float(np.median(step_ms)),
+                              "max": float(np.max(step_ms)), "drain_ms": ms_total - step_marks[-1]},
             "clocks": clocks,
             "e2e": {"value": rois_per_step / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "host_numa": numa,
                     "bound": "PCIe: %.2f GB of fp32 features cross the host link per step and GPU (the device part is %.2f ms)" % (h2d_bytes / 1e9, ms_step),
@@ -976,14 +993,15 @@ def run_train(args):
             dist.all_reduce(flat)
         return loss
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
         torch.cuda.synchronize()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.window_begin()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     for _ in range(args.steps):
