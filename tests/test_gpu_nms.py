@@ -179,3 +179,25 @@ def test_select_topk_matches_numpy(sorted_input):
             assert np.array_equal(got[:, 1:], boxes[want])
             assert np.array_equal(sc[i * top_n:i * top_n + n].cpu().numpy(), scores[want])
             assert np.all(rois[i * top_n + n:(i + 1) * top_n, 1:].cpu().numpy() == 0)
+
+
+@pytest.mark.parametrize("lens", [[1500, 900, 2048], [40] * 60 + [700], [600, 600]])
+def test_nms_default_dispatch_keep_all(lens):
+    """The library's own choice of path (test hook mode 0): keep-all calls over long segments go to the bitmask
+    kernels, many short segments (or max_keep) to the fused kernel -- the keep lists are the oracle's either way."""
+    from cvpr22_cross_modal_pseudo_labeling_b200 import _ext
+    from cvpr22_cross_modal_pseudo_labeling_b200.layers import nms_batched
+    rng = np.random.default_rng(len(lens))
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    bs, ss = zip(*[synth.make_nms_boxes(rng, n) for n in lens])
+    boxes, scores = np.concatenate(bs), np.concatenate(ss)
+    _ext.debug_nms(0)
+    for max_keep in (-1, 100):
+        want_idx, want_cnt = oracle.nms_batched(boxes, scores, off, 0.6, max_keep)
+        gi, gc = nms_batched(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(),
+                             torch.from_numpy(off.astype(np.int32)).cuda(), 0.6, max_keep, max(lens))
+        gi, gc = gi.cpu().numpy(), gc.cpu().numpy()
+        assert np.array_equal(gc, want_cnt)
+        for s in range(len(lens)):
+            a, k = off[s], want_cnt[s]
+            assert np.array_equal(gi[a:a + k], want_idx[a:a + k]), (s, max_keep)
